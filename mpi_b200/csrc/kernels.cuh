@@ -1,0 +1,802 @@
+// kernels.cuh -- sm_100a device code of libb200mpi: the data plane that replaces the
+// reference's gob-over-TCP Send/Receive (/root/reference/network.go:518-625) and implements the
+// collectives the reference only stubs (/root/reference/mpi.go:130).
+//
+// Memory model.  Every rank owns one cuMem heap; all heaps are mapped into every rank's address
+// space (Comm::base[r]) so a kernel reaches rank r's memory with plain ld/st.global that the
+// GPU routes over NVLink 5 / NVSwitch (or stays local when r is this rank or shares the device).
+// The first kCtrlBytes of each heap are control words:
+//     Slot slots[kMaxBlocks][kMaxRanks]   cross-rank flag + per-call buffer descriptor
+//     u32  ring[kMaxBlocks]               ring step counters
+// A collective kernel is   sync_start -> body -> sync_end   where both syncs are per-CTA
+// barriers between the CTAs with the same blockIdx on every rank (flag writes with
+// st.release.sys into the peer's slot, ld.acquire.sys spins on the own slot).  sync_start also
+// carries this rank's {send,recv} heap offsets for the call, so user buffers may sit at
+// different offsets on different ranks.  Epochs only grow; comparisons are wrap-safe.
+//
+// Reduction order (what oracle/collectives.c restates, bit for bit):
+//   one-shot / two-shot : acc = x_0; acc = op(acc, x_r) for r = 1..n-1          ("rank order")
+//   one-shot shuffle    : pairwise tree ((x0+x1)+(x2+x3))+((x4+x5)+(x6+x7))      ("tree order")
+//   ring                : chunk c: ((x_c + x_{c+1}) + ...) + x_{c-1}  (cyclic from c) ("ring order")
+//   nvls                : order chosen by the switch (tolerance-checked for floats, exact for ints)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200 {
+
+constexpr int kMaxRanks = 8;
+constexpr int kMaxBlocks = 592;            // 148 SMs x 4
+constexpr size_t kCtrlBytes = 2u << 20;    // control region at the start of every heap
+constexpr size_t kRingFlagsOff = 512u << 10;
+constexpr int kThreads = 512;
+
+struct __align__(32) Slot {
+  uint32_t flag;
+  uint32_t pad;
+  uint64_t a; // send offset of the writer for this call
+  uint64_t b; // recv offset
+  uint64_t c;
+};
+static_assert(sizeof(Slot) == 32, "slot size");
+static_assert(sizeof(Slot) * kMaxBlocks * kMaxRanks <= kRingFlagsOff, "control region layout");
+
+struct Comm {
+  char* base[kMaxRanks];     // heap of rank r as mapped in this process
+  char* mc;                  // multicast (NVLS) mapping of all heaps, or nullptr
+  uint32_t* status;          // host-mapped word: != 0 after a device-side watchdog timeout
+  unsigned long long timeout_ns;
+  int rank, n;
+  uint32_t epoch;            // start barrier value; end barrier uses epoch + 1
+};
+
+// ---------------------------------------------------------------------------------------------
+// flag primitives
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_u64(uint64_t* p, uint64_t v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_relaxed_sys_u64(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Spin until *p >= want (wrap-safe).  On watchdog expiry raises the host-visible status word
+// and gives up so the kernel can drain; the host then reports B200MPI_ERR_TIMEOUT.
+__device__ __forceinline__ void wait_flag(const uint32_t* p, uint32_t want, const Comm& c) {
+  unsigned long long t0 = 0;
+  uint32_t it = 0;
+  while ((int32_t)(ld_acquire_sys(p) - want) < 0) {
+    if ((++it & 0xfffu) == 0) {
+      unsigned long long now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (c.timeout_ns && now - t0 > c.timeout_ns) {
+        *(volatile uint32_t*)c.status = 1u;
+        __threadfence_system();
+        return;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ Slot* slot_of(const Comm& c, int owner, int block, int src) {
+  return reinterpret_cast<Slot*>(c.base[owner]) + (size_t)block * kMaxRanks + src;
+}
+
+// Per-CTA barrier #1: announce {a,b} to every rank, wait for everyone's, publish them in smem.
+__device__ __forceinline__ void sync_start(const Comm& c, uint64_t a, uint64_t b, uint64_t* s_a,
+                                           uint64_t* s_b) {
+  const int t = threadIdx.x;
+  if (t < c.n) {
+    Slot* theirs = slot_of(c, t, blockIdx.x, c.rank);
+    st_relaxed_sys_u64(&theirs->a, a);
+    st_relaxed_sys_u64(&theirs->b, b);
+    st_release_sys(&theirs->flag, c.epoch);
+    Slot* mine = slot_of(c, c.rank, blockIdx.x, t);
+    wait_flag(&mine->flag, c.epoch, c);
+    s_a[t] = ld_relaxed_sys_u64(&mine->a);
+    s_b[t] = ld_relaxed_sys_u64(&mine->b);
+  }
+  __syncthreads();
+}
+
+// Per-CTA barrier #2: all of this CTA's stores (local, peer and multicast) are released to every
+// rank, and every rank's matching CTA has finished reading/writing this rank's buffers.
+__device__ __forceinline__ void sync_end(const Comm& c) {
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (t < c.n) {
+    st_release_sys(&slot_of(c, t, blockIdx.x, c.rank)->flag, c.epoch + 1);
+    wait_flag(&slot_of(c, c.rank, blockIdx.x, t)->flag, c.epoch + 1, c);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 16-byte packs
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct alignas(16) Pack {
+  static constexpr int N = 16 / sizeof(T);
+  T v[N];
+};
+
+__device__ __forceinline__ uint4 ldg16(const void* p) { // streaming 128-bit load (local or peer)
+  uint4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void stg16(void* p, uint4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w)
+               : "memory");
+}
+template <typename T>
+__device__ __forceinline__ Pack<T> ld_pack(const void* p) {
+  union { uint4 u; Pack<T> k; } x;
+  x.u = ldg16(p);
+  return x.k;
+}
+__device__ __forceinline__ uint4 ldg16_sys(const void* p) { // coherent at system scope: never served from L1
+  uint4 r;
+  asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+template <typename T>
+__device__ __forceinline__ Pack<T> ld_pack_sys(const void* p) {
+  union { uint4 u; Pack<T> k; } x;
+  x.u = ldg16_sys(p);
+  return x.k;
+}
+template <typename T>
+__device__ __forceinline__ void st_pack(void* p, const Pack<T>& v) {
+  union { uint4 u; Pack<T> k; } x;
+  x.k = v;
+  stg16(p, x.u);
+}
+
+struct OpSum {
+  template <typename T> __device__ __forceinline__ static T apply(T a, T b) { return a + b; }
+};
+template <> __device__ __forceinline__ long long OpSum::apply<long long>(long long a, long long b) {
+  return (long long)((unsigned long long)a + (unsigned long long)b); // Go int64 wrap-around
+}
+struct OpMax {
+  template <typename T> __device__ __forceinline__ static T apply(T a, T b) { return b > a ? b : a; }
+};
+struct OpMin {
+  template <typename T> __device__ __forceinline__ static T apply(T a, T b) { return b < a ? b : a; }
+};
+
+template <typename T, typename Op>
+__device__ __forceinline__ Pack<T> combine(const Pack<T>& a, const Pack<T>& b) {
+  Pack<T> r;
+#pragma unroll
+  for (int i = 0; i < Pack<T>::N; ++i) r.v[i] = Op::template apply<T>(a.v[i], b.v[i]);
+  return r;
+}
+
+__device__ __forceinline__ bool all_aligned16(const uint64_t* s_a, const uint64_t* s_b, int n) {
+  uint64_t m = 0;
+  for (int r = 0; r < n; ++r) m |= s_a[r] | s_b[r];
+  return (m & 15) == 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Allreduce, one-shot: every rank reads all n buffers and keeps the whole result (latency path).
+// ---------------------------------------------------------------------------------------------
+template <typename T, typename Op, int NR>
+__global__ void __launch_bounds__(kThreads, 1)
+allreduce_oneshot_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t count) {
+  __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
+  sync_start(c, send_off, recv_off, s_a, s_b);
+  const int n = NR ? NR : c.n;
+  const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t gstride = (size_t)gridDim.x * blockDim.x;
+  char* out = c.base[c.rank] + s_b[c.rank];
+  if (all_aligned16(s_a, s_b, n)) {
+    constexpr int EPV = Pack<T>::N;
+    const size_t nvec = count / EPV;
+    for (size_t i = gtid; i < nvec; i += gstride) {
+      Pack<T> v[NR ? NR : kMaxRanks];
+#pragma unroll
+      for (int r = 0; r < (NR ? NR : kMaxRanks); ++r)
+        if (r < n) v[r] = ld_pack<T>(c.base[r] + s_a[r] + i * 16);
+      Pack<T> acc = v[0];
+#pragma unroll
+      for (int r = 1; r < (NR ? NR : kMaxRanks); ++r)
+        if (r < n) acc = combine<T, Op>(acc, v[r]);
+      st_pack<T>(out + i * 16, acc);
+    }
+    for (size_t e = nvec * EPV + gtid; e < count; e += gstride) {
+      T acc = reinterpret_cast<const T*>(c.base[0] + s_a[0])[e];
+      for (int r = 1; r < n; ++r) acc = Op::template apply<T>(acc, reinterpret_cast<const T*>(c.base[r] + s_a[r])[e]);
+      reinterpret_cast<T*>(out)[e] = acc;
+    }
+  } else {
+    for (size_t e = gtid; e < count; e += gstride) {
+      T acc = reinterpret_cast<const volatile T*>(c.base[0] + s_a[0])[e];
+      for (int r = 1; r < n; ++r) acc = Op::template apply<T>(acc, reinterpret_cast<const volatile T*>(c.base[r] + s_a[r])[e]);
+      reinterpret_cast<T*>(out)[e] = acc;
+    }
+  }
+  sync_end(c);
+}
+
+// One-shot with a lane per peer and warp-shuffle partial sums (n = 2, 4, 8; tree order).
+// 32/NR vectors per warp step; all NR peer loads of one vector are issued by different lanes in
+// the same instruction, so a small message costs one NVLink round trip.
+template <typename T, typename Op, int NR>
+__global__ void __launch_bounds__(kThreads, 1)
+allreduce_oneshot_shfl_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t count) {
+  __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
+  __shared__ const char* s_src[kMaxRanks];
+  sync_start(c, send_off, recv_off, s_a, s_b);
+  if (threadIdx.x < NR) s_src[threadIdx.x] = c.base[threadIdx.x] + s_a[threadIdx.x];
+  __syncthreads();
+  constexpr int EPV = Pack<T>::N;
+  constexpr int VPW = 32 / NR; // vectors per warp step
+  const int lane = threadIdx.x & 31;
+  const int peer = lane % NR, sub = lane / NR;
+  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  char* out = c.base[c.rank] + s_b[c.rank];
+  const bool al = all_aligned16(s_a, s_b, NR);
+  const size_t nvec = al ? count / EPV : 0;
+  const char* src = s_src[peer];
+  for (size_t base = warp * VPW; base < nvec; base += nwarps * VPW) {
+    const size_t i = base + sub;
+    const bool valid = i < nvec;
+    Pack<T> v;
+    if (valid) v = ld_pack<T>(src + i * 16);
+    else
+      for (int k = 0; k < EPV; ++k) v.v[k] = T(0);
+#pragma unroll
+    for (int m = 1; m < NR; m <<= 1) {
+      Pack<T> o;
+      union { Pack<T> k; uint32_t w[4]; } a, b;
+      a.k = v;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) b.w[w] = __shfl_xor_sync(0xffffffffu, a.w[w], m);
+      o = b.k;
+      v = (peer & m) ? combine<T, Op>(o, v) : combine<T, Op>(v, o); // lower ranks on the left
+    }
+    if (peer == 0 && valid) st_pack<T>(out + i * 16, v);
+  }
+  // scalar tail (and the whole message when some buffer is not 16-byte aligned), tree order too
+  const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t gstride = (size_t)gridDim.x * blockDim.x;
+  for (size_t e = nvec * EPV + gtid; e < count; e += gstride) {
+    T x[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) x[r] = reinterpret_cast<const volatile T*>(s_src[r])[e];
+#pragma unroll
+    for (int m = 1; m < NR; m <<= 1)
+#pragma unroll
+      for (int r = 0; r < NR; r += 2 * m) x[r] = Op::template apply<T>(x[r], x[r + m]);
+    reinterpret_cast<T*>(out)[e] = x[0];
+  }
+  sync_end(c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Allreduce, two-shot fused in one pass: rank j owns slice j; it loads the slice from all n
+// ranks (7 concurrent NVLink read streams + 1 local), reduces in rank order and stores the result
+// into every rank's recv buffer (7 NVLink write streams + 1 local).  Reduce-scatter and
+// all-gather traffic therefore overlap in both link directions and no mid barrier is needed.
+// In-place is safe: slice j of every buffer is read and then written only by rank j.
+// ---------------------------------------------------------------------------------------------
+template <typename T, typename Op, int NR, int UNROLL>
+__global__ void __launch_bounds__(kThreads, 1)
+allreduce_twoshot_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t count) {
+  __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
+  sync_start(c, send_off, recv_off, s_a, s_b);
+  const int n = NR ? NR : c.n;
+  constexpr int R = NR ? NR : kMaxRanks;
+  constexpr int EPV = Pack<T>::N;
+  const size_t tid = threadIdx.x;
+  if (all_aligned16(s_a, s_b, n)) {
+    const size_t nvec = count / EPV;
+    const size_t per = (nvec + n - 1) / n;
+    const size_t lo = per * c.rank < nvec ? per * c.rank : nvec;
+    const size_t hi = lo + per < nvec ? lo + per : nvec;
+    const char* src[R];
+    char* dst[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int q = r < n ? r : 0;
+      src[r] = c.base[q] + s_a[q];
+      // stores start at the next rank so the eight ranks do not all hit the same target at once
+      const int w = (c.rank + 1 + r) % n;
+      dst[r] = c.base[w] + s_b[w];
+    }
+    const size_t step = (size_t)gridDim.x * blockDim.x * UNROLL;
+    for (size_t i0 = lo + (size_t)blockIdx.x * blockDim.x * UNROLL + tid; i0 < hi; i0 += step) {
+      Pack<T> v[UNROLL][R];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const size_t i = i0 + (size_t)u * blockDim.x;
+        if (i < hi) {
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+            if (r < n) v[u][r] = ld_pack<T>(src[r] + i * 16);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const size_t i = i0 + (size_t)u * blockDim.x;
+        if (i < hi) {
+          Pack<T> acc = v[u][0];
+#pragma unroll
+          for (int r = 1; r < R; ++r)
+            if (r < n) acc = combine<T, Op>(acc, v[u][r]);
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+            if (r < n) st_pack<T>(dst[r] + i * 16, acc);
+        }
+      }
+    }
+    // elements past the last whole vector: reduced and pushed by the last rank
+    if (c.rank == n - 1) {
+      const size_t gtid = (size_t)blockIdx.x * blockDim.x + tid;
+      for (size_t e = nvec * EPV + gtid; e < count; e += (size_t)gridDim.x * blockDim.x) {
+        T acc = reinterpret_cast<const volatile T*>(c.base[0] + s_a[0])[e];
+        for (int r = 1; r < n; ++r) acc = Op::template apply<T>(acc, reinterpret_cast<const volatile T*>(c.base[r] + s_a[r])[e]);
+        for (int r = 0; r < n; ++r) reinterpret_cast<volatile T*>(c.base[r] + s_b[r])[e] = acc;
+      }
+    }
+  } else {
+    // unaligned buffers: same ownership by element, scalar accesses
+    const size_t per = (count + n - 1) / n;
+    const size_t lo = per * c.rank < count ? per * c.rank : count;
+    const size_t hi = lo + per < count ? lo + per : count;
+    for (size_t e = lo + (size_t)blockIdx.x * blockDim.x + tid; e < hi; e += (size_t)gridDim.x * blockDim.x) {
+      T acc = reinterpret_cast<const volatile T*>(c.base[0] + s_a[0])[e];
+      for (int r = 1; r < n; ++r) acc = Op::template apply<T>(acc, reinterpret_cast<const volatile T*>(c.base[r] + s_a[r])[e]);
+      for (int r = 0; r < n; ++r) reinterpret_cast<volatile T*>(c.base[r] + s_b[r])[e] = acc;
+    }
+  }
+  sync_end(c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Allreduce, ring: n-1 reduce-scatter steps then n-1 all-gather steps; each rank only ever loads
+// from its predecessor.  CTA b of rank r depends only on CTA b of rank r-1 (same vector subset on
+// every rank), signalled through ring[b] in the successor's heap.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t* ring_flag(const Comm& c, int owner, int block) {
+  return reinterpret_cast<uint32_t*>(c.base[owner] + kRingFlagsOff) + block;
+}
+
+template <typename T, typename Op>
+__global__ void __launch_bounds__(kThreads, 1)
+allreduce_ring_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t count) {
+  __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
+  sync_start(c, send_off, recv_off, s_a, s_b);
+  const int n = c.n, r = c.rank;
+  const int prev = (r + n - 1) % n, next = (r + 1) % n;
+  constexpr int EPV = Pack<T>::N;
+  const bool al = all_aligned16(s_a, s_b, n);
+  // Chunks are made of whole 16-byte groups whatever the alignment, so the summation order is a
+  // function of (count, n, dtype) only; the count % EPV tail is reduced in rank order.
+  const size_t groups = count / EPV;
+  const size_t per = (groups + n - 1) / n;
+  const char* my_send = c.base[r] + s_a[r];
+  char* my_recv = c.base[r] + s_b[r];
+  const char* prev_send = c.base[prev] + s_a[prev];
+  const char* prev_recv = c.base[prev] + s_b[prev];
+  const uint32_t fbase = c.epoch * 8u;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const int steps = 2 * (n - 1);
+  for (int g = 0; g < steps; ++g) {
+    const bool rs = g < n - 1;
+    const int s = rs ? g : g - (n - 1);
+    const int chunk = rs ? (r - s - 1 + 2 * n) % n : (r - s + 2 * n) % n;
+    if (g > 0) {
+      if (threadIdx.x == 0) wait_flag(ring_flag(c, r, blockIdx.x), fbase + (uint32_t)g, c);
+      __syncthreads();
+    }
+    const size_t lo = per * chunk < groups ? per * chunk : groups;
+    const size_t hi = lo + per < groups ? lo + per : groups;
+    const char* in = (g == 0) ? prev_send : prev_recv;
+    if (al) {
+      for (size_t i = lo + tid; i < hi; i += stride) {
+        Pack<T> p = ld_pack_sys<T>(in + i * 16);
+        if (rs) {
+          Pack<T> m = ld_pack<T>(my_send + i * 16);
+          p = combine<T, Op>(p, m);
+        }
+        st_pack<T>(my_recv + i * 16, p);
+      }
+    } else {
+      for (size_t e = lo * EPV + tid; e < hi * EPV; e += stride) {
+        T p = reinterpret_cast<const volatile T*>(in)[e];
+        if (rs) p = Op::template apply<T>(p, reinterpret_cast<const volatile T*>(my_send)[e]);
+        reinterpret_cast<volatile T*>(my_recv)[e] = p;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_sys(ring_flag(c, next, blockIdx.x), fbase + (uint32_t)g + 1u);
+  }
+  // tail: at most EPV-1 elements, one per thread of CTA 0, kept in a register across the barrier
+  const size_t te = groups * EPV + tid;
+  T tail = T(0);
+  if (te < count) {
+    tail = reinterpret_cast<const volatile T*>(c.base[0] + s_a[0])[te];
+    for (int q = 1; q < n; ++q) tail = Op::template apply<T>(tail, reinterpret_cast<const volatile T*>(c.base[q] + s_a[q])[te]);
+  }
+  sync_end(c);
+  // after the barrier nobody reads this rank's send buffer any more (in-place safe)
+  if (te < count) reinterpret_cast<T*>(my_recv)[te] = tail;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Allreduce through the switch (NVLS): rank j reduces slice j with multimem.ld_reduce (the
+// NVSwitch fetches the slice from all n heaps and returns the reduced value) and multicasts the
+// result into every rank's recv buffer with multimem.st.  Needs every rank to use the same heap
+// offsets (checked after sync_start; otherwise falls back to the two-shot body by returning 0).
+// ---------------------------------------------------------------------------------------------
+template <typename T, typename Op> struct Multimem;
+template <> struct Multimem<float, OpSum> {
+  __device__ __forceinline__ static Pack<float> ld_reduce(const void* p) {
+    Pack<float> r;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "l"(p) : "memory");
+    return r;
+  }
+};
+template <> struct Multimem<double, OpSum> {
+  __device__ __forceinline__ static Pack<double> ld_reduce(const void* p) {
+    Pack<double> r;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f64 %0, [%1];" : "=d"(r.v[0]) : "l"(p) : "memory");
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f64 %0, [%1];" : "=d"(r.v[1]) : "l"((const char*)p + 8) : "memory");
+    return r;
+  }
+};
+template <> struct Multimem<long long, OpSum> {
+  __device__ __forceinline__ static Pack<long long> ld_reduce(const void* p) {
+    Pack<long long> r;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.u64 %0, [%1];" : "=l"(r.v[0]) : "l"(p) : "memory");
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.u64 %0, [%1];" : "=l"(r.v[1]) : "l"((const char*)p + 8) : "memory");
+    return r;
+  }
+};
+template <> struct Multimem<long long, OpMax> {
+  __device__ __forceinline__ static Pack<long long> ld_reduce(const void* p) {
+    Pack<long long> r;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.max.s64 %0, [%1];" : "=l"(r.v[0]) : "l"(p) : "memory");
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.max.s64 %0, [%1];" : "=l"(r.v[1]) : "l"((const char*)p + 8) : "memory");
+    return r;
+  }
+};
+template <> struct Multimem<long long, OpMin> {
+  __device__ __forceinline__ static Pack<long long> ld_reduce(const void* p) {
+    Pack<long long> r;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.min.s64 %0, [%1];" : "=l"(r.v[0]) : "l"(p) : "memory");
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.min.s64 %0, [%1];" : "=l"(r.v[1]) : "l"((const char*)p + 8) : "memory");
+    return r;
+  }
+};
+__device__ __forceinline__ void multimem_st16(void* p, uint4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p),
+               "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)),
+               "f"(__uint_as_float(v.w))
+               : "memory");
+}
+
+template <typename T, typename Op, int UNROLL>
+__global__ void __launch_bounds__(kThreads, 1)
+allreduce_nvls_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t count) {
+  __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
+  sync_start(c, send_off, recv_off, s_a, s_b);
+  const int n = c.n;
+  constexpr int EPV = Pack<T>::N;
+  bool symmetric = ((send_off | recv_off) & 15) == 0;
+  for (int r = 0; r < n; ++r) symmetric = symmetric && s_a[r] == send_off && s_b[r] == recv_off;
+  const size_t tid = threadIdx.x;
+  const size_t nvec = symmetric ? count / EPV : 0;
+  if (symmetric) {
+    const size_t per = (nvec + n - 1) / n;
+    const size_t lo = per * c.rank < nvec ? per * c.rank : nvec;
+    const size_t hi = lo + per < nvec ? lo + per : nvec;
+    const char* src = c.mc + send_off;
+    char* dst = c.mc + recv_off;
+    const size_t step = (size_t)gridDim.x * blockDim.x * UNROLL;
+    for (size_t i0 = lo + (size_t)blockIdx.x * blockDim.x * UNROLL + tid; i0 < hi; i0 += step) {
+      Pack<T> v[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const size_t i = i0 + (size_t)u * blockDim.x;
+        if (i < hi) v[u] = Multimem<T, Op>::ld_reduce(src + i * 16);
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const size_t i = i0 + (size_t)u * blockDim.x;
+        if (i < hi) {
+          union { uint4 u4; Pack<T> k; } x;
+          x.k = v[u];
+          multimem_st16(dst + i * 16, x.u4);
+        }
+      }
+    }
+  }
+  // tail elements, or everything when the buffers are not symmetric: last rank, rank order, P2P
+  if (c.rank == n - 1 || !symmetric) {
+    const size_t per = symmetric ? 0 : (count + n - 1) / n;
+    const size_t lo = symmetric ? nvec * EPV : (per * c.rank < count ? per * c.rank : count);
+    const size_t hi = symmetric ? count : (lo + per < count ? lo + per : count);
+    for (size_t e = lo + (size_t)blockIdx.x * blockDim.x + tid; e < hi; e += (size_t)gridDim.x * blockDim.x) {
+      T acc = reinterpret_cast<const volatile T*>(c.base[0] + s_a[0])[e];
+      for (int r = 1; r < n; ++r) acc = Op::template apply<T>(acc, reinterpret_cast<const volatile T*>(c.base[r] + s_a[r])[e]);
+      for (int r = 0; r < n; ++r) reinterpret_cast<volatile T*>(c.base[r] + s_b[r])[e] = acc;
+    }
+  }
+  sync_end(c);
+}
+
+// Coherent (system-scope) loads of one access unit, for data that a peer rewrites during the
+// same kernel (ring steps): never served from a stale L1 line.
+__device__ __forceinline__ uint4 ld_unit_sys(const volatile uint4* p) { return ldg16_sys((const void*)p); }
+__device__ __forceinline__ unsigned long long ld_unit_sys(const volatile unsigned long long* p) { return *p; }
+__device__ __forceinline__ unsigned int ld_unit_sys(const volatile unsigned int* p) { return *p; }
+__device__ __forceinline__ unsigned char ld_unit_sys(const volatile unsigned char* p) { return *p; }
+
+// ---------------------------------------------------------------------------------------------
+// Allgather / Bcast bodies.  U is the access unit the host picked from ITS offsets and the size;
+// after sync_start every rank's offsets are known, and a rank that sees a less aligned peer
+// drops to the byte-wide instance of the same body.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool all_aligned_to(const uint64_t* s_a, const uint64_t* s_b, int n, unsigned unit) {
+  uint64_t m = 0;
+  for (int r = 0; r < n; ++r) m |= s_a[r] | s_b[r];
+  return (m & (unit - 1)) == 0;
+}
+
+// Direct push: every rank streams its block once from local HBM and stores it into all n recv
+// buffers (own copy skipped when the call is in place).
+template <typename U, int UNROLL>
+__device__ __forceinline__ void allgather_push_body(const Comm& c, const uint64_t* s_a, const uint64_t* s_b,
+                                                    size_t bytes_per_rank) {
+  const int n = c.n;
+  const size_t units = bytes_per_rank / sizeof(U);
+  const U* src = reinterpret_cast<const U*>(c.base[c.rank] + s_a[c.rank]);
+  const bool inplace = s_a[c.rank] == s_b[c.rank] + (uint64_t)c.rank * bytes_per_rank;
+  U* dst[kMaxRanks];
+#pragma unroll
+  for (int r = 0; r < kMaxRanks; ++r) {
+    const int w = (c.rank + 1 + r) % n; // w == rank when r == n-1
+    dst[r] = reinterpret_cast<U*>(c.base[w] + s_b[w] + (size_t)c.rank * bytes_per_rank);
+  }
+  const int ntargets = inplace ? n - 1 : n;
+  const size_t step = (size_t)gridDim.x * blockDim.x * UNROLL;
+  for (size_t i0 = (size_t)blockIdx.x * blockDim.x * UNROLL + threadIdx.x; i0 < units; i0 += step) {
+    U v[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const size_t i = i0 + (size_t)u * blockDim.x;
+      if (i < units) v[u] = src[i];
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const size_t i = i0 + (size_t)u * blockDim.x;
+      if (i < units) {
+#pragma unroll
+        for (int r = 0; r < kMaxRanks; ++r)
+          if (r < ntargets) dst[r][i] = v[u];
+      }
+    }
+  }
+}
+
+template <typename U, int UNROLL>
+__global__ void __launch_bounds__(kThreads, 1)
+allgather_push_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t bytes_per_rank) {
+  __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
+  sync_start(c, send_off, recv_off, s_a, s_b);
+  if (sizeof(U) == 1 || all_aligned_to(s_a, s_b, c.n, sizeof(U))) allgather_push_body<U, UNROLL>(c, s_a, s_b, bytes_per_rank);
+  else allgather_push_body<unsigned char, 1>(c, s_a, s_b, bytes_per_rank);
+  sync_end(c);
+}
+
+// Ring allgather: step s pulls block (r - s - 1) from the predecessor.
+template <typename U>
+__device__ __forceinline__ void allgather_ring_body(const Comm& c, const uint64_t* s_a, const uint64_t* s_b,
+                                                    size_t bytes_per_rank) {
+  const int n = c.n, r = c.rank;
+  const int prev = (r + n - 1) % n, next = (r + 1) % n;
+  const size_t units = bytes_per_rank / sizeof(U);
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  char* my_recv = c.base[r] + s_b[r];
+  const uint32_t fbase = c.epoch * 8u;
+  if (s_a[r] != s_b[r] + (uint64_t)r * bytes_per_rank) { // own block, out of place
+    const U* s = reinterpret_cast<const U*>(c.base[r] + s_a[r]);
+    U* d = reinterpret_cast<U*>(my_recv + (size_t)r * bytes_per_rank);
+    for (size_t i = tid; i < units; i += stride) d[i] = s[i];
+  }
+  for (int s = 0; s < n - 1; ++s) {
+    const int blk = (r - s - 1 + 2 * n) % n;
+    if (s > 0) {
+      if (threadIdx.x == 0) wait_flag(ring_flag(c, r, blockIdx.x), fbase + (uint32_t)s, c);
+      __syncthreads();
+    }
+    const volatile U* in = (s == 0) ? reinterpret_cast<const volatile U*>(c.base[prev] + s_a[prev])
+                                    : reinterpret_cast<const volatile U*>(c.base[prev] + s_b[prev] + (size_t)blk * bytes_per_rank);
+    U* out = reinterpret_cast<U*>(my_recv + (size_t)blk * bytes_per_rank);
+    for (size_t i = tid; i < units; i += stride) out[i] = ld_unit_sys(in + i);
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_sys(ring_flag(c, next, blockIdx.x), fbase + (uint32_t)s + 1u);
+  }
+}
+
+template <typename U>
+__global__ void __launch_bounds__(kThreads, 1)
+allgather_ring_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t bytes_per_rank) {
+  __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
+  sync_start(c, send_off, recv_off, s_a, s_b);
+  if (sizeof(U) == 1 || all_aligned_to(s_a, s_b, c.n, sizeof(U))) allgather_ring_body<U>(c, s_a, s_b, bytes_per_rank);
+  else allgather_ring_body<unsigned char>(c, s_a, s_b, bytes_per_rank);
+  sync_end(c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bcast
+// ---------------------------------------------------------------------------------------------
+// mode 0 (one-shot): every non-root pulls the whole buffer from root (root egress (n-1)*S).
+// mode 1 (two-shot, fused): non-root k pulls slice k from root and stores it locally and into
+// the other non-roots, so root sends every byte once and all links run in both directions.
+template <typename U, int UNROLL>
+__device__ __forceinline__ void bcast_body(const Comm& c, const uint64_t* s_a, size_t bytes, int root, int mode) {
+  const int n = c.n;
+  if (c.rank == root) return;
+  const size_t units = bytes / sizeof(U);
+  const U* src = reinterpret_cast<const U*>(c.base[root] + s_a[root]);
+  size_t lo = 0, hi = units;
+  int ntargets = 1;
+  U* dst[kMaxRanks];
+  dst[0] = reinterpret_cast<U*>(c.base[c.rank] + s_a[c.rank]);
+  if (mode == 1) {
+    const int m = n - 1;
+    const int k = c.rank < root ? c.rank : c.rank - 1;
+    const size_t per = (units + m - 1) / m;
+    lo = per * k < units ? per * k : units;
+    hi = lo + per < units ? lo + per : units;
+    for (int j = 1; j < n; ++j) { // other non-roots, starting after me
+      const int w = (c.rank + j) % n;
+      if (w == root) continue;
+      dst[ntargets++] = reinterpret_cast<U*>(c.base[w] + s_a[w]);
+    }
+  }
+  for (int j = ntargets; j < kMaxRanks; ++j) dst[j] = dst[0];
+  const size_t step = (size_t)gridDim.x * blockDim.x * UNROLL;
+  for (size_t i0 = lo + (size_t)blockIdx.x * blockDim.x * UNROLL + threadIdx.x; i0 < hi; i0 += step) {
+    U v[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const size_t i = i0 + (size_t)u * blockDim.x;
+      if (i < hi) v[u] = src[i];
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const size_t i = i0 + (size_t)u * blockDim.x;
+      if (i < hi) {
+#pragma unroll
+        for (int r = 0; r < kMaxRanks; ++r)
+          if (r < ntargets) dst[r][i] = v[u];
+      }
+    }
+  }
+}
+
+template <typename U, int UNROLL>
+__global__ void __launch_bounds__(kThreads, 1)
+bcast_kernel(Comm c, uint64_t buf_off, size_t bytes, int root, int mode) {
+  __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
+  sync_start(c, buf_off, buf_off, s_a, s_b);
+  if (sizeof(U) == 1 || all_aligned_to(s_a, s_b, c.n, sizeof(U))) bcast_body<U, UNROLL>(c, s_a, bytes, root, mode);
+  else bcast_body<unsigned char, 1>(c, s_a, bytes, root, mode);
+  sync_end(c);
+}
+
+// Bcast through the switch: root streams its buffer once into the multicast address.
+template <int UNROLL>
+__global__ void __launch_bounds__(kThreads, 1)
+bcast_nvls_kernel(Comm c, uint64_t buf_off, size_t bytes, int root) {
+  __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
+  sync_start(c, buf_off, buf_off, s_a, s_b);
+  const int n = c.n;
+  bool symmetric = (buf_off & 15) == 0 && (bytes & 15) == 0;
+  for (int r = 0; r < n; ++r) symmetric = symmetric && s_a[r] == buf_off;
+  if (symmetric) {
+    if (c.rank == root) {
+      const size_t nvec = bytes / 16;
+      const char* src = c.base[root] + buf_off;
+      char* dst = c.mc + buf_off;
+      const size_t step = (size_t)gridDim.x * blockDim.x * UNROLL;
+      for (size_t i0 = (size_t)blockIdx.x * blockDim.x * UNROLL + threadIdx.x; i0 < nvec; i0 += step) {
+        uint4 v[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          const size_t i = i0 + (size_t)u * blockDim.x;
+          if (i < nvec) v[u] = ldg16(src + i * 16);
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          const size_t i = i0 + (size_t)u * blockDim.x;
+          if (i < nvec) multimem_st16(dst + i * 16, v[u]);
+        }
+      }
+    }
+  } else if (c.rank != root) { // asymmetric buffers: pull bytes from root
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(c.base[root] + s_a[root]);
+    unsigned char* dst = reinterpret_cast<unsigned char*>(c.base[c.rank] + buf_off);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < bytes; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+  }
+  sync_end(c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Point-to-point and local copies: dst <- src, `bytes` bytes, any alignment.  src may be a peer
+// mapping (receiver pulls the sender's posted region over NVLink).
+// ---------------------------------------------------------------------------------------------
+template <int UNROLL>
+__global__ void __launch_bounds__(kThreads, 1)
+copy_bytes_kernel(unsigned char* __restrict__ dst, const unsigned char* __restrict__ src, size_t bytes) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const uintptr_t da = reinterpret_cast<uintptr_t>(dst), sa = reinterpret_cast<uintptr_t>(src);
+  if (((da ^ sa) & 15) == 0) {
+    size_t head = (16 - (da & 15)) & 15;
+    if (head > bytes) head = bytes;
+    for (size_t i = tid; i < head; i += stride) dst[i] = src[i];
+    const size_t nvec = (bytes - head) / 16;
+    const unsigned char* s = src + head;
+    unsigned char* d = dst + head;
+    const size_t step = stride * UNROLL;
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x * UNROLL + threadIdx.x; i0 < nvec; i0 += step) {
+      uint4 v[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const size_t i = i0 + (size_t)u * blockDim.x;
+        if (i < nvec) v[u] = ldg16(s + i * 16);
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const size_t i = i0 + (size_t)u * blockDim.x;
+        if (i < nvec) stg16(d + i * 16, v[u]);
+      }
+    }
+    for (size_t i = head + nvec * 16 + tid; i < bytes; i += stride) dst[i] = src[i];
+  } else {
+    for (size_t i = tid; i < bytes; i += stride) dst[i] = src[i];
+  }
+}
+
+// A device-wide rendezvous with nothing in between (b200mpi_barrier).
+__global__ void barrier_kernel(Comm c) {
+  __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
+  sync_start(c, 0, 0, s_a, s_b);
+  sync_end(c);
+}
+
+} // namespace b200
