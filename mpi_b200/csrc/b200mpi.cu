@@ -177,10 +177,13 @@ static int grid_for(size_t units_per_rank, int unroll) {
   return (int)(want > (size_t)cap ? cap : want);
 }
 
-static Comm next_comm() {
+// mids: number of flag values reserved between the start and the end barrier (in-place one-shot
+// rounds).  Every rank computes it from (count, grid) only, so epochs stay in step.
+static Comm next_comm(uint32_t mids = 0) {
   Comm c = g->comm;
   c.epoch = g->epoch;
-  g->epoch += 2;
+  c.end_epoch = g->epoch + 1 + mids;
+  g->epoch += 2 + mids;
   return c;
 }
 
@@ -211,28 +214,13 @@ static int launch_copy(void* dst, const void* src, size_t bytes, cudaStream_t s)
 // kernel dispatch
 // ---------------------------------------------------------------------------------------------
 template <typename T, typename Op>
-static int launch_allreduce_t(int algo, const Comm& c, uint64_t so, uint64_t ro, size_t count, cudaStream_t s) {
+static int launch_allreduce_body_t(int algo, const Comm& c, uint64_t so, uint64_t ro, size_t count, cudaStream_t s) {
   const int n = c.n;
   constexpr int EPV = 16 / sizeof(T);
   const size_t nvec = (count + EPV - 1) / EPV;
+  const size_t per = (nvec + n - 1) / n;
   switch (algo) {
-    case B200MPI_ALGO_ONESHOT: {
-      if ((n == 2 || n == 4 || n == 8) && nvec <= 4096) { // lane-per-peer + warp shuffle
-        int blocks = grid_for(nvec * n, 1);
-        if (n == 2) allreduce_oneshot_shfl_kernel<T, Op, 2><<<blocks, kThreads, 0, s>>>(c, so, ro, count);
-        else if (n == 4) allreduce_oneshot_shfl_kernel<T, Op, 4><<<blocks, kThreads, 0, s>>>(c, so, ro, count);
-        else allreduce_oneshot_shfl_kernel<T, Op, 8><<<blocks, kThreads, 0, s>>>(c, so, ro, count);
-        return launch_check("allreduce_oneshot_shfl_kernel");
-      }
-      int blocks = grid_for(nvec, 1);
-      if (n == 2) allreduce_oneshot_kernel<T, Op, 2><<<blocks, kThreads, 0, s>>>(c, so, ro, count);
-      else if (n == 4) allreduce_oneshot_kernel<T, Op, 4><<<blocks, kThreads, 0, s>>>(c, so, ro, count);
-      else if (n == 8) allreduce_oneshot_kernel<T, Op, 8><<<blocks, kThreads, 0, s>>>(c, so, ro, count);
-      else allreduce_oneshot_kernel<T, Op, 0><<<blocks, kThreads, 0, s>>>(c, so, ro, count);
-      return launch_check("allreduce_oneshot_kernel");
-    }
     case B200MPI_ALGO_TWOSHOT: {
-      const size_t per = (nvec + n - 1) / n;
       if (n == 2) { allreduce_twoshot_kernel<T, Op, 2, 8><<<grid_for(per, 8), kThreads, 0, s>>>(c, so, ro, count); }
       else if (n == 4) { allreduce_twoshot_kernel<T, Op, 4, 4><<<grid_for(per, 4), kThreads, 0, s>>>(c, so, ro, count); }
       else if (n == 8) { allreduce_twoshot_kernel<T, Op, 8, 2><<<grid_for(per, 2), kThreads, 0, s>>>(c, so, ro, count); }
@@ -240,7 +228,6 @@ static int launch_allreduce_t(int algo, const Comm& c, uint64_t so, uint64_t ro,
       return launch_check("allreduce_twoshot_kernel");
     }
     case B200MPI_ALGO_RING: {
-      const size_t per = (nvec + n - 1) / n;
       allreduce_ring_kernel<T, Op><<<grid_for(per, 4), kThreads, 0, s>>>(c, so, ro, count);
       return launch_check("allreduce_ring_kernel");
     }
@@ -249,7 +236,37 @@ static int launch_allreduce_t(int algo, const Comm& c, uint64_t so, uint64_t ro,
 }
 
 template <typename T, typename Op>
-static int launch_allreduce_nvls_t(const Comm& c, uint64_t so, uint64_t ro, size_t count, cudaStream_t s) {
+static int launch_allreduce_t(int algo, uint64_t so, uint64_t ro, size_t count, cudaStream_t s) {
+  const int n = g->ctrl.n;
+  constexpr int EPV = 16 / sizeof(T);
+  const size_t nvec = (count + EPV - 1) / EPV;
+  if (algo != B200MPI_ALGO_ONESHOT) {
+    const Comm c = next_comm();
+    return launch_allreduce_body_t<T, Op>(algo, c, so, ro, count, s);
+  }
+  // one-shot: reserve one mid-barrier value per round (upper bound: scalar rounds of the
+  // unaligned path, which has the most), see allreduce_oneshot_kernel
+  const bool shfl = (n == 2 || n == 4 || n == 8) && nvec <= 4096;
+  const int blocks = shfl ? grid_for(nvec * n, 1) : grid_for(nvec, 1);
+  const size_t per_round = (size_t)blocks * kThreads;
+  const size_t rounds = (count + per_round - 1) / per_round + (shfl ? (nvec * n + per_round - 1) / per_round : 0) + 2;
+  const Comm c = next_comm((uint32_t)rounds);
+  if (shfl) {
+    if (n == 2) allreduce_oneshot_shfl_kernel<T, Op, 2><<<blocks, kThreads, 0, s>>>(c, so, ro, count);
+    else if (n == 4) allreduce_oneshot_shfl_kernel<T, Op, 4><<<blocks, kThreads, 0, s>>>(c, so, ro, count);
+    else allreduce_oneshot_shfl_kernel<T, Op, 8><<<blocks, kThreads, 0, s>>>(c, so, ro, count);
+    return launch_check("allreduce_oneshot_shfl_kernel");
+  }
+  if (n == 2) allreduce_oneshot_kernel<T, Op, 2><<<blocks, kThreads, 0, s>>>(c, so, ro, count);
+  else if (n == 4) allreduce_oneshot_kernel<T, Op, 4><<<blocks, kThreads, 0, s>>>(c, so, ro, count);
+  else if (n == 8) allreduce_oneshot_kernel<T, Op, 8><<<blocks, kThreads, 0, s>>>(c, so, ro, count);
+  else allreduce_oneshot_kernel<T, Op, 0><<<blocks, kThreads, 0, s>>>(c, so, ro, count);
+  return launch_check("allreduce_oneshot_kernel");
+}
+
+template <typename T, typename Op>
+static int launch_allreduce_nvls_t(uint64_t so, uint64_t ro, size_t count, cudaStream_t s) {
+  const Comm c = next_comm();
   constexpr int EPV = 16 / sizeof(T);
   const size_t nvec = (count + EPV - 1) / EPV;
   const size_t per = (nvec + c.n - 1) / c.n;
@@ -262,20 +279,20 @@ static bool nvls_supports(int dtype, int op) {
   return dtype == B200MPI_I64; // min/max: integer only in the switch
 }
 
-static int launch_allreduce(int algo, int dtype, int op, const Comm& c, uint64_t so, uint64_t ro, size_t count, cudaStream_t s) {
+static int launch_allreduce(int algo, int dtype, int op, uint64_t so, uint64_t ro, size_t count, cudaStream_t s) {
   if (algo == B200MPI_ALGO_NVLS) {
-    if (dtype == B200MPI_F32 && op == B200MPI_SUM) return launch_allreduce_nvls_t<float, OpSum>(c, so, ro, count, s);
-    if (dtype == B200MPI_F64 && op == B200MPI_SUM) return launch_allreduce_nvls_t<double, OpSum>(c, so, ro, count, s);
-    if (dtype == B200MPI_I64 && op == B200MPI_SUM) return launch_allreduce_nvls_t<long long, OpSum>(c, so, ro, count, s);
-    if (dtype == B200MPI_I64 && op == B200MPI_MAX) return launch_allreduce_nvls_t<long long, OpMax>(c, so, ro, count, s);
-    if (dtype == B200MPI_I64 && op == B200MPI_MIN) return launch_allreduce_nvls_t<long long, OpMin>(c, so, ro, count, s);
+    if (dtype == B200MPI_F32 && op == B200MPI_SUM) return launch_allreduce_nvls_t<float, OpSum>(so, ro, count, s);
+    if (dtype == B200MPI_F64 && op == B200MPI_SUM) return launch_allreduce_nvls_t<double, OpSum>(so, ro, count, s);
+    if (dtype == B200MPI_I64 && op == B200MPI_SUM) return launch_allreduce_nvls_t<long long, OpSum>(so, ro, count, s);
+    if (dtype == B200MPI_I64 && op == B200MPI_MAX) return launch_allreduce_nvls_t<long long, OpMax>(so, ro, count, s);
+    if (dtype == B200MPI_I64 && op == B200MPI_MIN) return launch_allreduce_nvls_t<long long, OpMin>(so, ro, count, s);
     return fail(B200MPI_ERR_UNSUPPORTED, "allreduce: NVLS supports sum (f32,f64,i64) and min/max (i64) only");
   }
 #define B200_DISPATCH(T)                                                                         \
   switch (op) {                                                                                  \
-    case B200MPI_SUM: return launch_allreduce_t<T, OpSum>(algo, c, so, ro, count, s);            \
-    case B200MPI_MAX: return launch_allreduce_t<T, OpMax>(algo, c, so, ro, count, s);            \
-    case B200MPI_MIN: return launch_allreduce_t<T, OpMin>(algo, c, so, ro, count, s);            \
+    case B200MPI_SUM: return launch_allreduce_t<T, OpSum>(algo, so, ro, count, s);            \
+    case B200MPI_MAX: return launch_allreduce_t<T, OpMax>(algo, so, ro, count, s);            \
+    case B200MPI_MIN: return launch_allreduce_t<T, OpMin>(algo, so, ro, count, s);            \
   }                                                                                              \
   break;
   switch (dtype) {
@@ -443,8 +460,7 @@ static int do_allreduce(const void* send, void* recv, size_t count, int dtype, i
   else if (send == recv) out = in;
   else { rc = resolve_out(recv, bytes, memkind, 1, out); if (rc) return rc; }
   const int algo = pick_allreduce(bytes, dtype, op);
-  Comm c = next_comm();
-  rc = launch_allreduce(algo, dtype, op, c, in.off, out.off, count, g->stream);
+  rc = launch_allreduce(algo, dtype, op, in.off, out.off, count, g->stream);
   if (rc) return rc;
   rc = copy_out(recv, bytes, memkind, out);
   if (rc) return rc;

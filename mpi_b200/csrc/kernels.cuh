@@ -47,7 +47,8 @@ struct Comm {
   uint32_t* status;          // host-mapped word: != 0 after a device-side watchdog timeout
   unsigned long long timeout_ns;
   int rank, n;
-  uint32_t epoch;            // start barrier value; end barrier uses epoch + 1
+  uint32_t epoch;            // start barrier value
+  uint32_t end_epoch;        // end barrier value (epoch + 1 + number of reserved mid barriers)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -120,9 +121,21 @@ __device__ __forceinline__ void sync_end(const Comm& c) {
   __syncthreads();
   const int t = threadIdx.x;
   if (t < c.n) {
-    st_release_sys(&slot_of(c, t, blockIdx.x, c.rank)->flag, c.epoch + 1);
-    wait_flag(&slot_of(c, c.rank, blockIdx.x, t)->flag, c.epoch + 1, c);
+    st_release_sys(&slot_of(c, t, blockIdx.x, c.rank)->flag, c.end_epoch);
+    wait_flag(&slot_of(c, c.rank, blockIdx.x, t)->flag, c.end_epoch, c);
   }
+}
+
+// Per-CTA barrier between a read phase and a write phase of the same addresses (in-place
+// one-shot): `value` must lie strictly between c.epoch and c.end_epoch and grow from call to call.
+__device__ __forceinline__ void sync_mid(const Comm& c, uint32_t value) {
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (t < c.n) {
+    st_release_sys(&slot_of(c, t, blockIdx.x, c.rank)->flag, value);
+    wait_flag(&slot_of(c, c.rank, blockIdx.x, t)->flag, value, c);
+  }
+  __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -203,7 +216,16 @@ __device__ __forceinline__ bool all_aligned16(const uint64_t* s_a, const uint64_
 
 // ---------------------------------------------------------------------------------------------
 // Allreduce, one-shot: every rank reads all n buffers and keeps the whole result (latency path).
+// The work is cut into rounds of one unit per thread.  When any rank runs in place
+// (send == recv) a round is  read+reduce -> sync_mid -> write : nobody overwrites a value that a
+// peer has yet to read.  Out of place the mid barriers are skipped.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool any_inplace(const uint64_t* s_a, const uint64_t* s_b, int n) {
+  bool ip = false;
+  for (int r = 0; r < n; ++r) ip = ip || s_a[r] == s_b[r];
+  return ip;
+}
+
 template <typename T, typename Op, int NR>
 __global__ void __launch_bounds__(kThreads, 1)
 allreduce_oneshot_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t count) {
@@ -213,31 +235,37 @@ allreduce_oneshot_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t co
   const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t gstride = (size_t)gridDim.x * blockDim.x;
   char* out = c.base[c.rank] + s_b[c.rank];
-  if (all_aligned16(s_a, s_b, n)) {
-    constexpr int EPV = Pack<T>::N;
-    const size_t nvec = count / EPV;
-    for (size_t i = gtid; i < nvec; i += gstride) {
+  const bool inplace = any_inplace(s_a, s_b, n);
+  uint32_t mid = c.epoch + 1;
+  constexpr int EPV = Pack<T>::N;
+  const bool al = all_aligned16(s_a, s_b, n);
+  const size_t nvec = al ? count / EPV : 0;
+  for (size_t base = 0; base < nvec; base += gstride) {
+    const size_t i = base + gtid;
+    Pack<T> acc;
+    if (i < nvec) {
       Pack<T> v[NR ? NR : kMaxRanks];
 #pragma unroll
       for (int r = 0; r < (NR ? NR : kMaxRanks); ++r)
         if (r < n) v[r] = ld_pack<T>(c.base[r] + s_a[r] + i * 16);
-      Pack<T> acc = v[0];
+      acc = v[0];
 #pragma unroll
       for (int r = 1; r < (NR ? NR : kMaxRanks); ++r)
         if (r < n) acc = combine<T, Op>(acc, v[r]);
-      st_pack<T>(out + i * 16, acc);
     }
-    for (size_t e = nvec * EPV + gtid; e < count; e += gstride) {
-      T acc = reinterpret_cast<const T*>(c.base[0] + s_a[0])[e];
-      for (int r = 1; r < n; ++r) acc = Op::template apply<T>(acc, reinterpret_cast<const T*>(c.base[r] + s_a[r])[e]);
-      reinterpret_cast<T*>(out)[e] = acc;
-    }
-  } else {
-    for (size_t e = gtid; e < count; e += gstride) {
-      T acc = reinterpret_cast<const volatile T*>(c.base[0] + s_a[0])[e];
+    if (inplace) sync_mid(c, mid++);
+    if (i < nvec) st_pack<T>(out + i * 16, acc);
+  }
+  // scalar rounds: the count % EPV tail, or everything when some buffer is not 16-byte aligned
+  for (size_t base = nvec * EPV; base < count; base += gstride) {
+    const size_t e = base + gtid;
+    T acc = T(0);
+    if (e < count) {
+      acc = reinterpret_cast<const volatile T*>(c.base[0] + s_a[0])[e];
       for (int r = 1; r < n; ++r) acc = Op::template apply<T>(acc, reinterpret_cast<const volatile T*>(c.base[r] + s_a[r])[e]);
-      reinterpret_cast<T*>(out)[e] = acc;
     }
+    if (inplace) sync_mid(c, mid++);
+    if (e < count) reinterpret_cast<T*>(out)[e] = acc;
   }
   sync_end(c);
 }
@@ -261,10 +289,12 @@ allreduce_oneshot_shfl_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size
   const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
   char* out = c.base[c.rank] + s_b[c.rank];
   const bool al = all_aligned16(s_a, s_b, NR);
+  const bool inplace = any_inplace(s_a, s_b, NR);
+  uint32_t mid = c.epoch + 1;
   const size_t nvec = al ? count / EPV : 0;
   const char* src = s_src[peer];
-  for (size_t base = warp * VPW; base < nvec; base += nwarps * VPW) {
-    const size_t i = base + sub;
+  for (size_t round = 0; round < nvec; round += nwarps * VPW) { // uniform across the CTA
+    const size_t i = round + warp * VPW + sub;
     const bool valid = i < nvec;
     Pack<T> v;
     if (valid) v = ld_pack<T>(src + i * 16);
@@ -272,28 +302,31 @@ allreduce_oneshot_shfl_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size
       for (int k = 0; k < EPV; ++k) v.v[k] = T(0);
 #pragma unroll
     for (int m = 1; m < NR; m <<= 1) {
-      Pack<T> o;
       union { Pack<T> k; uint32_t w[4]; } a, b;
       a.k = v;
 #pragma unroll
       for (int w = 0; w < 4; ++w) b.w[w] = __shfl_xor_sync(0xffffffffu, a.w[w], m);
-      o = b.k;
-      v = (peer & m) ? combine<T, Op>(o, v) : combine<T, Op>(v, o); // lower ranks on the left
+      v = (peer & m) ? combine<T, Op>(b.k, v) : combine<T, Op>(v, b.k); // lower ranks on the left
     }
+    if (inplace) sync_mid(c, mid++);
     if (peer == 0 && valid) st_pack<T>(out + i * 16, v);
   }
-  // scalar tail (and the whole message when some buffer is not 16-byte aligned), tree order too
+  // scalar rounds (tail, or the whole message when unaligned), tree order too
   const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t gstride = (size_t)gridDim.x * blockDim.x;
-  for (size_t e = nvec * EPV + gtid; e < count; e += gstride) {
+  for (size_t base = nvec * EPV; base < count; base += gstride) {
+    const size_t e = base + gtid;
     T x[NR];
+    if (e < count) {
 #pragma unroll
-    for (int r = 0; r < NR; ++r) x[r] = reinterpret_cast<const volatile T*>(s_src[r])[e];
+      for (int r = 0; r < NR; ++r) x[r] = reinterpret_cast<const volatile T*>(s_src[r])[e];
 #pragma unroll
-    for (int m = 1; m < NR; m <<= 1)
+      for (int m = 1; m < NR; m <<= 1)
 #pragma unroll
-      for (int r = 0; r < NR; r += 2 * m) x[r] = Op::template apply<T>(x[r], x[r + m]);
-    reinterpret_cast<T*>(out)[e] = x[0];
+        for (int r = 0; r < NR; r += 2 * m) x[r] = Op::template apply<T>(x[r], x[r + m]);
+    }
+    if (inplace) sync_mid(c, mid++);
+    if (e < count) reinterpret_cast<T*>(out)[e] = x[0];
   }
   sync_end(c);
 }

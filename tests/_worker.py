@@ -1,0 +1,558 @@
+"""One rank of a test world.  Usage: _worker.py <scenario> --out FILE [scenario args] -mpi-* flags.
+Every scenario drives the product through the public mpi_b200 API / C ABI and checks results
+against the CPU oracle (oracle/), which is test infrastructure only."""
+import argparse
+import json
+import os
+import sys
+import threading
+import traceback
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import mpi_b200 as mpi  # noqa: E402
+from mpi_b200 import _lib as L  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+SEED = 0xB2000000
+DTYPES = {"f32": np.float32, "f64": np.float64, "i64": np.int64}
+ALGOS = {"auto": 0, "oneshot": 1, "twoshot": 2, "ring": 3, "nvls": 4}
+
+
+def inputs_for(dtype, n, count, salt=0):
+    return [O.fill(dtype, SEED + salt * 1000 + r, count) for r in range(n)]
+
+
+def expect_allreduce(ins, op, algo_used, n, count, dtype):
+    """The oracle order that matches the kernel the library ran."""
+    nvec = -(-count // (16 // np.dtype(dtype).itemsize))
+    if algo_used == L.ALGO_ONESHOT:
+        order = O.ORDER_TREE if (n in (2, 4, 8) and nvec <= 4096) else O.ORDER_RANK
+    elif algo_used == L.ALGO_RING:
+        order = O.ORDER_RING
+    elif algo_used == L.ALGO_NVLS:
+        order = O.ORDER_F64
+    else:
+        order = O.ORDER_RANK
+    return O.allreduce(ins, op=op, order=order), order
+
+
+TRACE = os.environ.get("B200MPI_TEST_TRACE")
+_T0 = None
+
+
+def trace(msg):
+    global _T0
+    if not TRACE:
+        return
+    import time
+    if _T0 is None:
+        _T0 = time.time()
+    with open("%s.rank%d" % (TRACE, mpi.Rank()), "a") as f:
+        f.write("%8.3f %s\n" % (time.time() - _T0, msg))
+
+
+def check_equal(got, want, what, exact=True, ins=None):
+    trace(what)
+    if exact:
+        same = np.array_equal(got.view(np.uint8), want.view(np.uint8))
+        if not same and got.dtype.kind == "f":
+            # NaN payloads may differ; compare values with NaN == NaN
+            same = np.array_equal(got, want, equal_nan=True)
+        if not same:
+            bad = np.flatnonzero(got != want)[:5]
+            raise AssertionError("%s: mismatch at %s got %s want %s" % (what, bad, got[bad], want[bad]))
+    else:
+        # |gpu - ref| <= 1e-6 * sum_r |x_r[i]|
+        scale = np.sum([np.abs(x.astype(np.float64)) for x in ins], axis=0)
+        err = np.abs(got.astype(np.float64) - want.astype(np.float64))
+        if not np.all(err <= 1e-6 * scale + 1e-300):
+            i = int(np.argmax(err - 1e-6 * scale))
+            raise AssertionError("%s: |err| %g > 1e-6*%g at %d" % (what, err[i], scale[i], i))
+
+
+def make_buffer(kind, arr):
+    """kind: 'heap' (DeviceSlice), 'host' (numpy)."""
+    if kind == "heap":
+        return mpi.Alloc(arr.size, arr.dtype).copy_from_host(arr)
+    return np.array(arr, copy=True)
+
+
+def read_buffer(buf):
+    return buf.to_host() if isinstance(buf, mpi.DeviceSlice) else buf
+
+
+def free_buffer(buf):
+    if isinstance(buf, mpi.DeviceSlice):
+        buf.free()
+
+
+# ------------------------------------------------------------------------------------------------
+def scenario_collectives(a):
+    lib = L.load()
+    rank, n = mpi.Rank(), mpi.Size()
+    sizes = [int(s) for s in a.sizes.split(",")]
+    dtypes = a.dtypes.split(",")
+    algos = a.algos.split(",")
+    kinds = a.kinds.split(",")
+    info = (L.ctypes.c_size_t(), L.ctypes.c_size_t(), L.ctypes.c_int())
+    lib.b200mpi_heap_info(L.ctypes.byref(info[0]), L.ctypes.byref(info[1]), L.ctypes.byref(info[2]))
+    nvls = bool(info[2].value)
+    done = 0
+    for kind in kinds:
+        for dn in dtypes:
+            dt = DTYPES[dn]
+            for count in sizes:
+                ins = inputs_for(dt, n, count, salt=count % 97)
+                for algo in algos:
+                    if algo == "nvls" and not nvls:
+                        continue
+                    if algo == "ring" and n == 1:
+                        continue
+                    lib.b200mpi_set_algo(L.COLL_ALLREDUCE, ALGOS[algo])
+                    used = lib.b200mpi_get_algo(L.COLL_ALLREDUCE, count, O.NP2DT[np.dtype(dt)]) if n > 1 else L.ALGO_TWOSHOT
+                    for inplace in (False, True):
+                        send = make_buffer(kind, ins[rank])
+                        recv = send if inplace else make_buffer(kind, np.zeros(count, dtype=dt))
+                        mpi.Allreduce(send, recv, mpi.SUM)
+                        got = read_buffer(recv)
+                        want, order = expect_allreduce(ins, O.SUM, used, n, count, dt)
+                        exact = dt == np.int64 or order != O.ORDER_F64
+                        check_equal(got, want, "allreduce %s %s n=%d count=%d algo=%s(%d) inplace=%s" % (kind, dn, n, count, algo, used, inplace), exact=exact, ins=ins)
+                        if not inplace:
+                            check_equal(read_buffer(send), ins[rank], "allreduce send buffer untouched")
+                            free_buffer(recv)
+                        free_buffer(send)
+                        done += 1
+                lib.b200mpi_set_algo(L.COLL_ALLREDUCE, 0)
+                # max / min once per dtype and size (default algorithm)
+                for op, oop in ((mpi.MAX, O.MAX), (mpi.MIN, O.MIN)):
+                    send = make_buffer(kind, ins[rank])
+                    recv = make_buffer(kind, np.zeros(count, dtype=dt))
+                    mpi.Allreduce(send, recv, op)
+                    check_equal(read_buffer(recv), O.allreduce(ins, op=oop), "allreduce op=%d %s count=%d" % (op, dn, count))
+                    free_buffer(send)
+                    free_buffer(recv)
+                    done += 1
+                # allgather: push and ring
+                for algo in ("auto", "ring"):
+                    lib.b200mpi_set_algo(L.COLL_ALLGATHER, ALGOS[algo])
+                    send = make_buffer(kind, ins[rank])
+                    recv = make_buffer(kind, np.full(count * n, -1, dtype=dt))
+                    mpi.Allgather(send, recv)
+                    check_equal(read_buffer(recv), O.allgather(ins), "allgather %s %s count=%d algo=%s" % (kind, dn, count, algo))
+                    free_buffer(send)
+                    free_buffer(recv)
+                    done += 1
+                lib.b200mpi_set_algo(L.COLL_ALLGATHER, 0)
+                # bcast from every root with every algorithm (root 0 and last only for big sizes)
+                roots = range(n) if count <= 4096 else sorted({0, n - 1})
+                for algo in ("oneshot", "twoshot", "nvls"):
+                    if algo == "nvls" and not nvls:
+                        continue
+                    lib.b200mpi_set_algo(L.COLL_BCAST, ALGOS[algo])
+                    for root in roots:
+                        buf = make_buffer(kind, ins[root] if rank == root else np.full(count, -1, dtype=dt).astype(dt))
+                        mpi.Bcast(buf, root)
+                        check_equal(read_buffer(buf), O.bcast(ins[root]), "bcast %s %s count=%d root=%d algo=%s" % (kind, dn, count, root, algo))
+                        free_buffer(buf)
+                        done += 1
+                lib.b200mpi_set_algo(L.COLL_BCAST, 0)
+    mpi.Barrier()
+    return {"checked": done, "nvls": nvls}
+
+
+def scenario_edge_values(a):
+    """f32 edge set {+-0, +-Inf, NaN, subnormal, 1e38} and i64 wrap-around."""
+    lib = L.load()
+    rank, n = mpi.Rank(), mpi.Size()
+    edge = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-45, -1e-45, 1e38, -1e38, 1.0, 3.4e38, 1.17549435e-38], dtype=np.float32)
+    count = edge.size * 8
+    ins = []
+    for r in range(n):
+        x = np.tile(edge, 8)
+        x = np.roll(x, r * 5)  # different pairings per rank: inf + -inf, 1e38 + 1e38 ...
+        ins.append(x.astype(np.float32))
+    done = 0
+    for algo in ("oneshot", "twoshot", "ring"):
+        if algo == "ring" and n == 1:
+            continue
+        lib.b200mpi_set_algo(L.COLL_ALLREDUCE, ALGOS[algo])
+        used = lib.b200mpi_get_algo(L.COLL_ALLREDUCE, count, L.F32) if n > 1 else L.ALGO_TWOSHOT
+        send = mpi.Alloc(count, np.float32).copy_from_host(ins[rank])
+        recv = mpi.Alloc(count, np.float32)
+        mpi.Allreduce(send, recv)
+        want, _ = expect_allreduce(ins, O.SUM, used, n, count, np.float32)
+        got = recv.to_host()
+        # NaN positions must agree, everything else bit-exact
+        if not np.array_equal(np.isnan(got), np.isnan(want)):
+            raise AssertionError("edge f32 %s: NaN pattern differs" % algo)
+        m = ~np.isnan(want)
+        check_equal(got[m], want[m], "edge f32 algo=%s" % algo)
+        send.free()
+        recv.free()
+        done += 1
+    lib.b200mpi_set_algo(L.COLL_ALLREDUCE, 0)
+    big = np.array([2**63 - 1, -2**63, 2**62, -1, 1, 0x7FFFFFFFFFFFFFF0, 123456789012345678, -987654321098765432], dtype=np.int64)
+    ins = [np.roll(np.tile(big, 33), r * 3) for r in range(n)]
+    for algo in ("oneshot", "twoshot", "ring", "nvls"):
+        if algo == "ring" and n == 1:
+            continue
+        lib.b200mpi_set_algo(L.COLL_ALLREDUCE, ALGOS[algo])
+        buf = mpi.Alloc(ins[0].size, np.int64).copy_from_host(ins[rank])
+        mpi.Allreduce(buf, buf)
+        check_equal(buf.to_host(), O.allreduce(ins), "i64 wrap algo=%s" % algo)
+        buf.free()
+        done += 1
+    lib.b200mpi_set_algo(L.COLL_ALLREDUCE, 0)
+    # all ranks must hold bit-identical floating results: gather everyone's result and compare
+    x = [O.fill(np.float32, SEED + 77 + r, 1000) for r in range(n)]
+    for algo in ("oneshot", "twoshot", "ring", "nvls"):
+        if algo == "ring" and n == 1:
+            continue
+        lib.b200mpi_set_algo(L.COLL_ALLREDUCE, ALGOS[algo])
+        res = np.zeros(1000, dtype=np.float32)
+        mpi.Allreduce(np.array(x[rank]), res)
+        allres = np.zeros(1000 * n, dtype=np.float32)
+        mpi.Allgather(res, allres)
+        for r in range(n):
+            check_equal(allres[r * 1000:(r + 1) * 1000], res, "rank %d result identical to mine (algo %s)" % (r, algo))
+        done += 1
+    lib.b200mpi_set_algo(L.COLL_ALLREDUCE, 0)
+    return {"checked": done}
+
+
+def scenario_unaligned(a):
+    """Offsets that are not 16-byte aligned and differ between ranks."""
+    lib = L.load()
+    rank, n = mpi.Rank(), mpi.Size()
+    done = 0
+    count = 1003
+    for dn, dt in DTYPES.items():
+        ins = inputs_for(dt, n, count, salt=5)
+        big = mpi.Alloc(count + 16, dt)
+        out = mpi.Alloc(count + 16, dt)
+        so = 1 + (rank % 3)  # element offsets: 4/8 byte granularity, rank dependent
+        ro = 1 + ((rank + 1) % 2)
+        send = big[so:so + count].copy_from_host(ins[rank])
+        recv = out[ro:ro + count]
+        for algo in ("oneshot", "twoshot", "ring"):
+            if algo == "ring" and n == 1:
+                continue
+            lib.b200mpi_set_algo(L.COLL_ALLREDUCE, ALGOS[algo])
+            used = lib.b200mpi_get_algo(L.COLL_ALLREDUCE, count, O.NP2DT[np.dtype(dt)]) if n > 1 else L.ALGO_TWOSHOT
+            mpi.Allreduce(send, recv)
+            want, _ = expect_allreduce(ins, O.SUM, used, n, count, dt)
+            if used == L.ALGO_ONESHOT and n in (2, 4, 8):
+                want = O.allreduce(ins, order=O.ORDER_TREE)
+            check_equal(recv.to_host(), want, "unaligned allreduce %s algo=%s" % (dn, algo))
+            done += 1
+        lib.b200mpi_set_algo(L.COLL_ALLREDUCE, 0)
+        gath = mpi.Alloc(count * n + 16, dt)
+        g = gath[ro:ro + count * n]
+        for algo in ("auto", "ring"):
+            lib.b200mpi_set_algo(L.COLL_ALLGATHER, ALGOS[algo])
+            mpi.Allgather(send, g)
+            check_equal(g.to_host(), O.allgather(ins), "unaligned allgather %s %s" % (dn, algo))
+            done += 1
+        lib.b200mpi_set_algo(L.COLL_ALLGATHER, 0)
+        for algo in ("oneshot", "twoshot"):
+            lib.b200mpi_set_algo(L.COLL_BCAST, ALGOS[algo])
+            b = big[so:so + count].copy_from_host(ins[1 % n] if rank == 1 % n else np.zeros(count, dtype=dt))
+            mpi.Bcast(b, 1 % n)
+            check_equal(b.to_host(), ins[1 % n], "unaligned bcast %s %s" % (dn, algo))
+            done += 1
+        lib.b200mpi_set_algo(L.COLL_BCAST, 0)
+        # bytes: odd length, odd offset
+        raw = np.frombuffer(O.fill(np.int64, SEED + rank, 200).tobytes(), dtype=np.uint8)[:1501]
+        rb = np.zeros(1501 * n, dtype=np.uint8)
+        mpi.Allgather(np.array(raw), rb)
+        want = np.concatenate([np.frombuffer(O.fill(np.int64, SEED + r, 200).tobytes(), dtype=np.uint8)[:1501] for r in range(n)])
+        check_equal(rb, want, "byte allgather")
+        big.free()
+        out.free()
+        gath.free()
+        done += 1
+    return {"checked": done}
+
+
+def scenario_p2p(a):
+    """bounce (examples/bounce/bounce.go:85-138): even/odd ping-pong over the size ladder, []byte then
+    []float64, equality checked on the even rank; plus device-resident buffers."""
+    rank, n = mpi.Rank(), mpi.Size()
+    if n % 2:
+        raise AssertionError("Must have an even number of nodes for this example")
+    even = rank % 2 == 0
+    lengths = [int(s) for s in a.sizes.split(",")]
+    maxlen = max(lengths + [8])
+    message = np.frombuffer(O.fill(np.int64, SEED + rank, maxlen // 8 + 1).tobytes(), dtype=np.uint8)[:maxlen].copy()
+    message_f = O.fill(np.float64, SEED + 100 + rank, maxlen // 8 + 1)
+    done = 0
+    for l in lengths:
+        for rep in range(2):
+            msg = message[:l]
+            rcv = np.zeros(l, dtype=np.uint8)
+            if even:
+                mpi.Send(msg, rank + 1, 0)
+                rcv = mpi.Receive(rcv, rank + 1, 0)
+                check_equal(rcv, msg, "bounce bytes len %d" % l)
+            else:
+                rcv = mpi.Receive(rcv, rank - 1, 0)
+                mpi.Send(rcv, rank - 1, 0)
+            msg_f = message_f[: l // 8]
+            rcv_f = np.zeros(l // 8, dtype=np.float64)
+            if even:
+                mpi.Send(msg_f, rank + 1, 0)
+                rcv_f = mpi.Receive(rcv_f, rank + 1, 0)
+                check_equal(rcv_f, msg_f, "bounce float64 len %d" % (l // 8))
+            else:
+                rcv_f = mpi.Receive(rcv_f, rank - 1, 0)
+                mpi.Send(rcv_f, rank - 1, 0)
+            done += 2
+        # device-resident: heap -> heap
+        cnt = l // 8
+        d_msg = mpi.Alloc(cnt, np.float64).copy_from_host(message_f[:cnt])
+        d_rcv = mpi.Alloc(cnt, np.float64)
+        if even:
+            mpi.Send(d_msg, rank + 1, 7)
+            got = mpi.Receive(d_rcv, rank + 1, 7)
+            if len(got) != cnt:
+                raise AssertionError("device recv count %d != %d" % (len(got), cnt))
+            check_equal(got.to_host(), message_f[:cnt], "bounce device float64 %d" % cnt)
+        else:
+            got = mpi.Receive(d_rcv, rank - 1, 7)
+            mpi.Send(got, rank - 1, 7)
+        d_msg.free()
+        d_rcv.free()
+        done += 1
+    # receive into a too-small buffer: the value still arrives whole (gob resize analogue)
+    if even:
+        mpi.Send(message_f[:1000], rank + 1, 11)
+    else:
+        got = mpi.Receive(np.zeros(10, dtype=np.float64), rank - 1, 11)
+        src = O.fill(np.float64, SEED + 100 + rank - 1, maxlen // 8 + 1)[:1000]
+        check_equal(got, src, "resize-on-receive")
+    # int64 and float32 typed slices
+    for dt in (np.int64, np.float32):
+        x = O.fill(dt, SEED + 5 + rank, 4097)
+        if even:
+            mpi.Send(x, rank + 1, 3)
+        else:
+            got = mpi.Receive(np.zeros(4097, dtype=dt), rank - 1, 3)
+            check_equal(got, O.fill(dt, SEED + 5 + rank - 1, 4097), "typed p2p %s" % np.dtype(dt).name)
+        done += 1
+    mpi.Barrier()
+    return {"checked": done}
+
+
+def scenario_helloworld(a):
+    """examples/helloworld/helloworld.go:54-81: every rank concurrently sends a string to every rank
+    (itself included) and receives from every rank, tag 0."""
+    rank, n = mpi.Rank(), mpi.Size()
+    errs, got = [], {}
+
+    def send(i):
+        try:
+            s = '"Hello node %d, I\'m node %d"' % (i, rank)
+            if i == rank:
+                s = '"I\'m just node %d talking to myself"' % rank
+            mpi.Send(s, i, 0)
+        except Exception as e:  # noqa: BLE001
+            errs.append("send %d: %s" % (i, e))
+
+    def recv(i):
+        try:
+            got[i] = mpi.Receive(str, i, 0)
+        except Exception as e:  # noqa: BLE001
+            errs.append("recv %d: %s" % (i, e))
+
+    ths = [threading.Thread(target=send, args=(i,)) for i in range(n)] + [threading.Thread(target=recv, args=(i,)) for i in range(n)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    if errs:
+        raise AssertionError("; ".join(errs))
+    for i in range(n):
+        want = '"Hello node %d, I\'m node %d"' % (rank, i) if i != rank else '"I\'m just node %d talking to myself"' % rank
+        if got.get(i) != want:
+            raise AssertionError("from %d got %r want %r" % (i, got.get(i), want))
+    return {"checked": n}
+
+
+def scenario_tags(a):
+    """Concurrent sends with distinct tags to one peer; duplicate in-flight tag -> TagExists."""
+    rank, n = mpi.Rank(), mpi.Size()
+    peer = rank ^ 1
+    ntags = 6
+    payloads = {t: O.fill(np.int64, SEED + 31 * t + rank, 100 + 37 * t) for t in range(ntags)}
+    errs, got = [], {}
+
+    def send(t):
+        try:
+            mpi.Send(payloads[t], peer, t)
+        except Exception as e:  # noqa: BLE001
+            errs.append("send tag %d: %r" % (t, e))
+
+    def recv(t):
+        try:
+            got[t] = mpi.Receive(np.zeros(1000, dtype=np.int64), peer, t)
+        except Exception as e:  # noqa: BLE001
+            errs.append("recv tag %d: %r" % (t, e))
+
+    # receivers start in reverse tag order so matching is really by tag
+    ths = [threading.Thread(target=send, args=(t,)) for t in range(ntags)] + [threading.Thread(target=recv, args=(t,)) for t in reversed(range(ntags))]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    if errs:
+        raise AssertionError("; ".join(errs))
+    for t in range(ntags):
+        check_equal(got[t], O.fill(np.int64, SEED + 31 * t + peer, 100 + 37 * t), "tag %d" % t)
+    mpi.Barrier()
+    # duplicate tag: second Send on the same {dest, tag} while the first is still unmatched
+    dup = {}
+    if rank == 0:
+        first = threading.Thread(target=lambda: mpi.Send(np.arange(4, dtype=np.int64), 1, 99))
+        first.start()
+        import time
+        time.sleep(0.3)
+        try:
+            mpi.Send(np.arange(4, dtype=np.int64), 1, 99)
+            dup["raised"] = False
+        except mpi.TagExists as e:
+            dup["raised"] = True
+            dup["tag"] = e.Tag
+        mpi.Send(np.arange(1, dtype=np.int64), 1, 100)  # tell rank 1 to go on
+        first.join()
+        if not dup.get("raised") or dup.get("tag") != 99:
+            raise AssertionError("duplicate tag did not raise TagExists: %s" % dup)
+    elif rank == 1:
+        mpi.Receive(np.zeros(1, dtype=np.int64), 0, 100)
+        got99 = mpi.Receive(np.zeros(4, dtype=np.int64), 0, 99)
+        check_equal(got99, np.arange(4, dtype=np.int64), "message behind duplicate tag")
+    mpi.Barrier()
+    return {"checked": ntags + 1}
+
+
+def scenario_fullsize(a):
+    """Full-size points checked through size-independent properties plus the oracle on the same
+    seeded inputs (the oracle finishes these sizes in a second or two)."""
+    lib = L.load()
+    rank, n = mpi.Rank(), mpi.Size()
+    done = 0
+    if a.what == "allgather":
+        count = 1 << 20  # "1M indices per rank" (BASELINE.json configs[4]); also the decimal million
+        for cnt in (count, 1000000):
+            mine = O.fill(np.int64, SEED + rank, cnt)
+            send = mpi.Alloc(cnt, np.int64).copy_from_host(mine)
+            recv = mpi.Alloc(cnt * n, np.int64)
+            for algo in ("auto", "ring"):
+                lib.b200mpi_set_algo(L.COLL_ALLGATHER, ALGOS[algo])
+                mpi.Allgather(send, recv)
+                got = recv.to_host()
+                for r in range(n):
+                    check_equal(got[r * cnt:(r + 1) * cnt], O.fill(np.int64, SEED + r, cnt), "allgather i64 %d block %d algo %s" % (cnt, r, algo))
+                done += 1
+            lib.b200mpi_set_algo(L.COLL_ALLGATHER, 0)
+            send.free()
+            recv.free()
+    else:
+        count = 1 << 24
+        ins = [O.fill(np.float32, SEED + r, count) for r in range(n)]
+        send = mpi.Alloc(count, np.float32).copy_from_host(ins[rank])
+        recv = mpi.Alloc(count, np.float32)
+        for algo in ("twoshot", "ring", "oneshot", "nvls"):
+            lib.b200mpi_set_algo(L.COLL_ALLREDUCE, ALGOS[algo])
+            used = lib.b200mpi_get_algo(L.COLL_ALLREDUCE, count, L.F32)
+            mpi.Allreduce(send, recv)
+            want, order = expect_allreduce(ins, O.SUM, used, n, count, np.float32)
+            check_equal(recv.to_host(), want, "allreduce f32 16Mi algo=%s" % algo, exact=order != O.ORDER_F64, ins=ins)
+            # linearity: allreduce(2x) == 2 * allreduce(x) exactly (scaling by 2 is exact in binary fp)
+            twice = mpi.Alloc(count, np.float32).copy_from_host(ins[rank] * np.float32(2))
+            mpi.Allreduce(twice, twice)
+            check_equal(twice.to_host(), want * np.float32(2), "linearity algo=%s" % algo, exact=order != O.ORDER_F64, ins=[x * 2 for x in ins])
+            twice.free()
+            done += 2
+        lib.b200mpi_set_algo(L.COLL_ALLREDUCE, 0)
+        # bcast 64 MiB from rank n-1, both P2P algorithms
+        for algo in ("oneshot", "twoshot", "nvls"):
+            lib.b200mpi_set_algo(L.COLL_BCAST, ALGOS[algo])
+            buf = mpi.Alloc(count, np.float32).copy_from_host(ins[n - 1] if rank == n - 1 else np.zeros(count, dtype=np.float32))
+            mpi.Bcast(buf, n - 1)
+            check_equal(buf.to_host(), ins[n - 1], "bcast 64MiB algo=%s" % algo)
+            buf.free()
+            done += 1
+        lib.b200mpi_set_algo(L.COLL_BCAST, 0)
+        send.free()
+        recv.free()
+    return {"checked": done}
+
+
+def scenario_smoke(a):
+    rank, n = mpi.Rank(), mpi.Size()
+    x = O.fill(np.float32, SEED + rank, 1 << 12)
+    out = np.zeros_like(x)
+    mpi.Allreduce(x, out)
+    want = O.allreduce([O.fill(np.float32, SEED + r, 1 << 12) for r in range(n)], order=O.ORDER_TREE if n in (2, 4, 8) else O.ORDER_RANK)
+    check_equal(out, want, "smoke allreduce")
+    return {"checked": 1, "device": L.load().b200mpi_device(), "launches": int(L.load().b200mpi_launch_count())}
+
+
+def scenario_control_only(a):
+    """CPU plumbing: bootstrap over TCP loopback, rank/size, barrier; data calls must refuse."""
+    rank, n = mpi.Rank(), mpi.Size()
+    lib = L.load()
+    rc = lib.b200mpi_barrier()
+    if rc:
+        raise AssertionError("control-plane barrier failed: %s" % L.last_error())
+    x = np.zeros(4, dtype=np.float32)
+    try:
+        mpi.Allreduce(x, x)
+        raise AssertionError("data call succeeded without a device")
+    except mpi.MpiError as e:
+        if e.code != L.ERR_NO_DEVICE:
+            raise
+    return {"checked": 1, "rank": rank, "size": n}
+
+
+SCENARIOS = {k[len("scenario_"):]: v for k, v in list(globals().items()) if k.startswith("scenario_")}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("scenario")
+    ap.add_argument("--out", required=True)
+    ap.add_argument("--sizes", default="0,1,3,4,5,255,256,257,4096,65537")
+    ap.add_argument("--dtypes", default="f32,f64,i64")
+    ap.add_argument("--algos", default="oneshot,twoshot,ring,nvls")
+    ap.add_argument("--kinds", default="heap,host")
+    ap.add_argument("--gpu", type=int, default=None)
+    ap.add_argument("--what", default="allgather")
+    ap.add_argument("--control-only", action="store_true")
+    args, rest = ap.parse_known_args()
+    sys.argv = [sys.argv[0]] + rest  # leave the -mpi-* flags for the library's flag parser
+    result = {"ok": False}
+    try:
+        gpu = -2 if args.control_only else args.gpu
+        mpi.api._reset_for_tests(mpi.Cuda(Gpu=gpu))
+        mpi.Init()
+        result.update(SCENARIOS[args.scenario](args))
+        result["rank_reported"] = mpi.Rank()
+        result["size_reported"] = mpi.Size()
+        mpi.Finalize()
+        result["ok"] = True
+    except Exception as e:  # noqa: BLE001
+        result["error"] = "%s: %s" % (type(e).__name__, e)
+        traceback.print_exc()
+    with open(args.out, "w") as f:
+        json.dump(result, f)
+    sys.exit(0 if result["ok"] else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,86 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every test launches a world of rank
+processes through the gompirun-style launcher and drives the product through the public API /
+C ABI; results are compared with the CPU oracle on the same seeded inputs.  When the box has fewer
+GPUs than ranks, ranks share device 0 (the kernels and the peer mappings are the same; the GPU
+time-slices between the processes)."""
+import os
+import subprocess
+
+import pytest
+
+from _launch import assert_world_ok, run_world
+
+pytestmark = pytest.mark.gpu
+ENV = {"B200MPI_WATCHDOG_S": "90"}
+
+
+def ngpus():
+    try:
+        return subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=30).stdout.count("GPU ")
+    except Exception:  # noqa: BLE001
+        return 0
+
+
+def world(n, scenario, *args, timeout=420, env=None):
+    e = dict(ENV)
+    if env:
+        e.update(env)
+    res = run_world(n, scenario, args=list(args), timeout=timeout, env=e)
+    assert_world_ok(res)
+    return res
+
+
+def test_smoke_world_of_1_and_2():
+    r1 = world(1, "smoke")
+    assert r1[0]["device"] == 0
+    r2 = world(2, "smoke")
+    assert all(r["launches"] >= 1 for r in r2)
+
+
+@pytest.mark.parametrize("n", [1, 2])
+def test_collectives_small_sizes_all_algorithms(n):
+    world(n, "collectives")
+
+
+def test_collectives_world_of_4():
+    world(4, "collectives", "--sizes", "0,1,5,257,65537", "--kinds", "heap")
+
+
+def test_collectives_world_of_3_generic_kernels():
+    world(3, "collectives", "--sizes", "3,257,4099", "--kinds", "heap,host")
+
+
+def test_collectives_world_of_8():
+    world(8, "collectives", "--sizes", "1,257,40001", "--kinds", "heap", "--dtypes", "f32,i64", timeout=600)
+
+
+@pytest.mark.parametrize("n", [2, 4])
+def test_edge_values_and_identical_results(n):
+    world(n, "edge_values")
+
+
+def test_unaligned_and_asymmetric_offsets():
+    world(2, "unaligned")
+    world(4, "unaligned")
+
+
+def test_bounce_send_receive():
+    # examples/bounce: the reference's size ladder (bounce.go:33) up to 1e7 bytes + the 1 MiB float64 point
+    world(2, "p2p", "--sizes", "0,1,10,100,1000,10000,100000,1000000,10000000,1048576", env={"B200MPI_STAGE_CHUNK": str(1 << 20)})
+    world(4, "p2p", "--sizes", "0,8,4096,1048576")
+
+
+@pytest.mark.parametrize("n", [1, 2, 4])
+def test_helloworld(n):
+    world(n, "helloworld")
+
+
+def test_concurrent_tags_and_duplicate_tag():
+    world(2, "tags")
+
+
+def test_full_size_points():
+    """BASELINE.json sizes: Allgather int64 1 Mi per rank x 8 ranks bit-exact; Allreduce f32 at 16 Mi
+    elements (64 MiB) with every algorithm; bounce 1 MiB float64 is covered above."""
+    world(8, "fullsize", "--what", "allgather", timeout=600, env={"B200MPI_HEAP_BYTES": str(512 << 20)})
+    world(2, "fullsize", "--what", "allreduce", timeout=600, env={"B200MPI_HEAP_BYTES": str(1 << 30)})
