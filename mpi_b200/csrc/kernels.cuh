@@ -479,6 +479,7 @@ allreduce_ring_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t count
     for (int q = 1; q < n; ++q) tail = Op::template apply<T>(tail, reinterpret_cast<const volatile T*>(c.base[q] + s_a[q])[te]);
   }
   sync_end(c);
+  __syncthreads(); // sync_end's waits are done by threads 0..n-1 only
   // after the barrier nobody reads this rank's send buffer any more (in-place safe)
   if (te < count) reinterpret_cast<T*>(my_recv)[te] = tail;
 }
