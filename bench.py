@@ -170,7 +170,7 @@ def main():
     lib = L.load()
     mpi.api._reset_for_tests(mpi.Cuda(Addr=addr, Addrs=addrs, Timeout=120 * 10**9, Gpu=local))
     mpi.Init()
-    algo_ids = {"auto": 0, "oneshot": 1, "twoshot": 2, "ring": 3, "nvls": 4}
+    algo_ids = {"auto": 0, "oneshot": 1, "twoshot": 2, "ring": 3, "nvls": 4, "smem": 5}
     lib.b200mpi_set_algo(L.COLL_ALLREDUCE, algo_ids[args.algo])
     from oracle import oracle as O  # input generator + parity spot check only
 

@@ -140,6 +140,9 @@ int b200mpi_stream_sync(void); /* waits and reports device-side watchdog errors 
 int b200mpi_set_algo(int coll, int algo); /* force an algorithm (benches, tests) */
 int b200mpi_get_algo(int coll, size_t count, int dtype); /* what AUTO resolves to (>=1) or <0 */
 int b200mpi_set_max_blocks(int blocks); /* cap grid size (0 = default: SMs x occupancy) */
+/* Tuning knobs for sweeps: "twoshot_unroll" (0|1), "nvls_unroll" (1|2|4|8), "nvls_min_ranks",
+ * "oneshot_max_bytes", "stage_chunk". */
+int b200mpi_set_param(const char* name, int64_t value);
 /* cudaStream_t used for collectives; set NULL to restore the library's own stream. */
 int b200mpi_get_stream(void** stream);
 int b200mpi_set_stream(void* stream);

@@ -50,6 +50,7 @@ SYMBOLS = {
     "b200mpi_set_algo": (_c.c_int, [_c.c_int, _c.c_int]),
     "b200mpi_get_algo": (_c.c_int, [_c.c_int, _c.c_size_t, _c.c_int]),
     "b200mpi_set_max_blocks": (_c.c_int, [_c.c_int]),
+    "b200mpi_set_param": (_c.c_int, [_c.c_char_p, _c.c_int64]),
     "b200mpi_get_stream": (_c.c_int, [_c.POINTER(_c.c_void_p)]),
     "b200mpi_set_stream": (_c.c_int, [_c.c_void_p]),
     "b200mpi_timer_start": (_c.c_int, []),

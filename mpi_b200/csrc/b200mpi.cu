@@ -18,6 +18,7 @@
 #include <sys/mman.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <mutex>
@@ -97,6 +98,9 @@ struct Ctx {
   size_t stage_off[2] = {0, 0}, stage_len[2] = {0, 0};
   std::atomic<int64_t> launches{0};
   size_t oneshot_max_bytes = 256u << 10;
+  int twoshot_unroll = 1; // 0: 1/2/4 vectors per thread for n = 8/4/2, 1: 2/4/8
+  int nvls_unroll = 4;
+  int nvls_min_ranks = 4; // below this the fused two-shot moves fewer bytes per link than NVLS
 };
 
 static Ctx* g = nullptr;
@@ -123,9 +127,14 @@ static size_t esize(int dtype) {
   return 0;
 }
 
+static thread_local int t_bound_dev = -1;
 static int need_data_plane() {
   if (!g || !g->initialised) return fail(B200MPI_ERR_NOT_INIT, "mpi: Init has not been called");
   if (g->control_only) return fail(B200MPI_ERR_NO_DEVICE, "no CUDA device bound (control-plane-only init); there is no CPU data path");
+  if (t_bound_dev != g->dev) { // the CUDA "current device" is per host thread; Send/Receive come from any goroutine/thread
+    if (cudaSetDevice(g->dev) != cudaSuccess) return fail(B200MPI_ERR_CUDA, "cudaSetDevice failed on a caller thread");
+    t_bound_dev = g->dev;
+  }
   return 0;
 }
 
@@ -221,15 +230,42 @@ static int launch_allreduce_body_t(int algo, const Comm& c, uint64_t so, uint64_
   const size_t per = (nvec + n - 1) / n;
   switch (algo) {
     case B200MPI_ALGO_TWOSHOT: {
-      if (n == 2) { allreduce_twoshot_kernel<T, Op, 2, 8><<<grid_for(per, 8), kThreads, 0, s>>>(c, so, ro, count); }
-      else if (n == 4) { allreduce_twoshot_kernel<T, Op, 4, 4><<<grid_for(per, 4), kThreads, 0, s>>>(c, so, ro, count); }
-      else if (n == 8) { allreduce_twoshot_kernel<T, Op, 8, 2><<<grid_for(per, 2), kThreads, 0, s>>>(c, so, ro, count); }
-      else { allreduce_twoshot_kernel<T, Op, 0, 2><<<grid_for(per, 2), kThreads, 0, s>>>(c, so, ro, count); }
+      if (g->twoshot_unroll) {
+        if (n == 2) { allreduce_twoshot_kernel<T, Op, 2, 8><<<grid_for(per, 8), kThreads, 0, s>>>(c, so, ro, count); }
+        else if (n == 4) { allreduce_twoshot_kernel<T, Op, 4, 4><<<grid_for(per, 4), kThreads, 0, s>>>(c, so, ro, count); }
+        else if (n == 8) { allreduce_twoshot_kernel<T, Op, 8, 2><<<grid_for(per, 2), kThreads, 0, s>>>(c, so, ro, count); }
+        else { allreduce_twoshot_kernel<T, Op, 0, 2><<<grid_for(per, 2), kThreads, 0, s>>>(c, so, ro, count); }
+      } else {
+        if (n == 2) { allreduce_twoshot_kernel<T, Op, 2, 4><<<grid_for(per, 4), kThreads, 0, s>>>(c, so, ro, count); }
+        else if (n == 4) { allreduce_twoshot_kernel<T, Op, 4, 2><<<grid_for(per, 2), kThreads, 0, s>>>(c, so, ro, count); }
+        else if (n == 8) { allreduce_twoshot_kernel<T, Op, 8, 1><<<grid_for(per, 1), kThreads, 0, s>>>(c, so, ro, count); }
+        else { allreduce_twoshot_kernel<T, Op, 0, 1><<<grid_for(per, 1), kThreads, 0, s>>>(c, so, ro, count); }
+      }
       return launch_check("allreduce_twoshot_kernel");
     }
     case B200MPI_ALGO_RING: {
       allreduce_ring_kernel<T, Op><<<grid_for(per, 4), kThreads, 0, s>>>(c, so, ro, count);
       return launch_check("allreduce_ring_kernel");
+    }
+    case B200MPI_ALGO_TWOSHOT_SMEM: {
+      const size_t tiles = (per * 16 + kSmemChunk - 1) / kSmemChunk;
+      int cap = g->max_blocks > 0 ? g->max_blocks : g->sm_count;
+      const int blocks = (int)std::max<size_t>(1, std::min<size_t>(tiles, (size_t)cap));
+#define B200_SMEM(NRV)                                                                                           \
+  {                                                                                                              \
+    const size_t smem = (size_t)(kSmemStages * NRV + kSmemOutStages) * kSmemChunk;                               \
+    static bool attr_set = false;                                                                                \
+    if (!attr_set) {                                                                                             \
+      cudaFuncSetAttribute(allreduce_twoshot_smem_kernel<T, Op, NRV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      attr_set = true;                                                                                           \
+    }                                                                                                            \
+    allreduce_twoshot_smem_kernel<T, Op, NRV><<<blocks, kSmemThreads, smem, s>>>(c, so, ro, count);              \
+  }
+      if (n == 2) B200_SMEM(2)
+      else if (n == 4) B200_SMEM(4)
+      else B200_SMEM(8)
+#undef B200_SMEM
+      return launch_check("allreduce_twoshot_smem_kernel");
     }
   }
   return fail(B200MPI_ERR_UNSUPPORTED, "allreduce: algorithm not available for this dtype/op");
@@ -270,7 +306,12 @@ static int launch_allreduce_nvls_t(uint64_t so, uint64_t ro, size_t count, cudaS
   constexpr int EPV = 16 / sizeof(T);
   const size_t nvec = (count + EPV - 1) / EPV;
   const size_t per = (nvec + c.n - 1) / c.n;
-  allreduce_nvls_kernel<T, Op, 4><<<grid_for(per, 4), kThreads, 0, s>>>(c, so, ro, count);
+  switch (g->nvls_unroll) {
+    case 1: allreduce_nvls_kernel<T, Op, 1><<<grid_for(per, 1), kThreads, 0, s>>>(c, so, ro, count); break;
+    case 2: allreduce_nvls_kernel<T, Op, 2><<<grid_for(per, 2), kThreads, 0, s>>>(c, so, ro, count); break;
+    case 8: allreduce_nvls_kernel<T, Op, 8><<<grid_for(per, 8), kThreads, 0, s>>>(c, so, ro, count); break;
+    default: allreduce_nvls_kernel<T, Op, 4><<<grid_for(per, 4), kThreads, 0, s>>>(c, so, ro, count); break;
+  }
   return launch_check("allreduce_nvls_kernel");
 }
 
@@ -306,11 +347,11 @@ static int launch_allreduce(int algo, int dtype, int op, uint64_t so, uint64_t r
 
 static int pick_allreduce(size_t bytes, int dtype, int op) {
   int forced = g->algo[B200MPI_COLL_ALLREDUCE];
-  if (forced == B200MPI_ALGO_TWOSHOT_SMEM) forced = B200MPI_ALGO_TWOSHOT; // staged variant: see DESIGN.md
+  if (forced == B200MPI_ALGO_TWOSHOT_SMEM && !(g->ctrl.n == 2 || g->ctrl.n == 4 || g->ctrl.n == 8)) forced = B200MPI_ALGO_TWOSHOT;
   if (forced == B200MPI_ALGO_NVLS && !(g->heap.mc_base && nvls_supports(dtype, op))) forced = 0;
   if (forced) return forced;
   if (bytes <= g->oneshot_max_bytes) return B200MPI_ALGO_ONESHOT;
-  if (g->heap.mc_base && nvls_supports(dtype, op)) return B200MPI_ALGO_NVLS;
+  if (g->heap.mc_base && nvls_supports(dtype, op) && g->ctrl.n >= g->nvls_min_ranks) return B200MPI_ALGO_NVLS;
   return B200MPI_ALGO_TWOSHOT;
 }
 
@@ -320,7 +361,7 @@ static int pick_bcast(size_t bytes) {
   if (forced == B200MPI_ALGO_RING || forced == B200MPI_ALGO_TWOSHOT_SMEM) forced = B200MPI_ALGO_TWOSHOT;
   if (forced) return forced;
   if (bytes <= g->oneshot_max_bytes || g->ctrl.n == 2) return B200MPI_ALGO_ONESHOT;
-  if (g->heap.mc_base && bytes % 16 == 0) return B200MPI_ALGO_NVLS;
+  if (g->heap.mc_base && bytes % 16 == 0 && g->ctrl.n >= g->nvls_min_ranks && getenv("B200MPI_BCAST_NVLS")) return B200MPI_ALGO_NVLS;
   return B200MPI_ALGO_TWOSHOT;
 }
 
@@ -932,6 +973,17 @@ int b200mpi_get_algo(int coll, size_t count, int dtype) {
   if (coll == B200MPI_COLL_BCAST) return pick_bcast(bytes);
   if (coll == B200MPI_COLL_ALLGATHER) return pick_allgather(bytes);
   return fail(B200MPI_ERR_ARG, "get_algo: bad collective id");
+}
+int b200mpi_set_param(const char* name, int64_t value) {
+  if (!g || !g->initialised) return fail(B200MPI_ERR_NOT_INIT, "mpi: Init has not been called");
+  std::string k = name ? name : "";
+  if (k == "twoshot_unroll") g->twoshot_unroll = value ? 1 : 0;
+  else if (k == "nvls_unroll") g->nvls_unroll = (int)value;
+  else if (k == "nvls_min_ranks") g->nvls_min_ranks = (int)value;
+  else if (k == "oneshot_max_bytes") g->oneshot_max_bytes = (size_t)value;
+  else if (k == "stage_chunk") g->stage_chunk = (size_t)std::max<int64_t>(value, 4096);
+  else return fail(B200MPI_ERR_ARG, "set_param: unknown parameter '" + k + "'");
+  return 0;
 }
 int b200mpi_set_max_blocks(int blocks) {
   if (!g || !g->initialised) return fail(B200MPI_ERR_NOT_INIT, "mpi: Init has not been called");

@@ -412,6 +412,149 @@ allreduce_twoshot_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t co
 }
 
 // ---------------------------------------------------------------------------------------------
+// Allreduce, two-shot with shared-memory staging (TMA bulk copies).  Same ownership, traffic and
+// rank-order arithmetic as allreduce_twoshot_kernel, but the SM's load/store units never touch
+// NVLink: one producer thread per CTA streams kChunk-byte tiles of slice j from all NR heaps into
+// a ring of shared-memory stages with cp.async.bulk (completion on an mbarrier); 8 consumer warps
+// reduce the NR tiles out of shared memory into an output tile, and one thread writes that tile
+// to all NR recv buffers with cp.async.bulk shared->global.  In flight per SM: kStages*NR*kChunk.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSmemChunk = 4096;       // bytes per tile per rank (256 consumer threads x 16 B)
+constexpr int kSmemStages = 4;
+constexpr int kSmemOutStages = 2;
+constexpr int kSmemConsumers = 256;
+constexpr int kSmemThreads = kSmemConsumers + 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <typename T, typename Op, int NR>
+__global__ void __launch_bounds__(kSmemThreads, 1)
+allreduce_twoshot_smem_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t count) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
+  __shared__ __align__(8) uint64_t full_bar[kSmemStages], empty_bar[kSmemStages];
+  unsigned char* in_tiles = smem_raw;                                         // [stage][rank][chunk]
+  unsigned char* out_tiles = smem_raw + (size_t)kSmemStages * NR * kSmemChunk; // [ostage][chunk]
+  sync_start(c, send_off, recv_off, s_a, s_b);
+  constexpr int EPV = Pack<T>::N;
+  const int tid = threadIdx.x;
+  const bool al = all_aligned16(s_a, s_b, NR);
+  const size_t nvec = al ? count / EPV : 0;
+  const size_t per = (nvec + NR - 1) / NR;
+  const size_t lo = per * c.rank < nvec ? per * c.rank : nvec;
+  const size_t hi = lo + per < nvec ? lo + per : nvec;
+  const size_t slice_bytes = (hi - lo) * 16;
+  const size_t ntiles = (slice_bytes + kSmemChunk - 1) / kSmemChunk;
+  if (tid == 0) {
+    for (int s = 0; s < kSmemStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kSmemConsumers / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid >= kSmemConsumers) {
+    // ---- producer warp: one lane drives the TMA loads ----
+    if (tid == kSmemConsumers) {
+      uint32_t it = 0;
+      for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int s = it % kSmemStages;
+        const uint32_t use = it / kSmemStages;
+        if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1);
+        const size_t off = lo * 16 + t * kSmemChunk;
+        const uint32_t bytes = (uint32_t)((slice_bytes - t * kSmemChunk) < (size_t)kSmemChunk ? (slice_bytes - t * kSmemChunk) : (size_t)kSmemChunk);
+        mbar_expect_tx(&full_bar[s], bytes * NR);
+#pragma unroll
+        for (int r = 0; r < NR; ++r)
+          bulk_g2s(in_tiles + ((size_t)s * NR + r) * kSmemChunk, c.base[r] + s_a[r] + off, bytes, &full_bar[s]);
+      }
+    }
+  } else {
+    // ---- consumer warps ----
+    uint32_t it = 0;
+    for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int s = it % kSmemStages;
+      const int os = it % kSmemOutStages;
+      const uint32_t bytes = (uint32_t)((slice_bytes - t * kSmemChunk) < (size_t)kSmemChunk ? (slice_bytes - t * kSmemChunk) : (size_t)kSmemChunk);
+      mbar_wait(&full_bar[s], (it / kSmemStages) & 1);
+      if (it >= (uint32_t)kSmemOutStages) { // the stores that read out_tiles[os] two tiles ago must have drained it
+        if (tid == 0) bulk_wait_read<kSmemOutStages - 1>();
+        asm volatile("bar.sync 1, %0;" ::"n"(kSmemConsumers) : "memory");
+      }
+      if ((uint32_t)tid * 16 < bytes) {
+        const unsigned char* src = in_tiles + (size_t)s * NR * kSmemChunk + (size_t)tid * 16;
+        Pack<T> acc = *reinterpret_cast<const Pack<T>*>(src);
+#pragma unroll
+        for (int r = 1; r < NR; ++r) acc = combine<T, Op>(acc, *reinterpret_cast<const Pack<T>*>(src + (size_t)r * kSmemChunk));
+        *reinterpret_cast<Pack<T>*>(out_tiles + (size_t)os * kSmemChunk + (size_t)tid * 16) = acc;
+      }
+      fence_proxy_async_smem(); // generic-proxy writes to out_tiles -> visible to the bulk-copy engine
+      asm volatile("bar.sync 1, %0;" ::"n"(kSmemConsumers) : "memory");
+      if ((tid & 31) == 0) mbar_arrive(&empty_bar[s]); // this warp is done reading in_tiles[s]
+      if (tid == 0) {
+        const size_t off = lo * 16 + t * kSmemChunk;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          const int w = (c.rank + 1 + r) % NR;
+          bulk_s2g(c.base[w] + s_b[w] + off, out_tiles + (size_t)os * kSmemChunk, bytes);
+        }
+        bulk_commit();
+      }
+    }
+    if (tid == 0) bulk_wait<0>(); // every peer write of this CTA has been performed
+  }
+  // elements outside whole 16-byte vectors, or everything when unaligned: scalar, last rank / by ownership
+  {
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + tid;
+    const size_t gstride = (size_t)gridDim.x * blockDim.x;
+    size_t elo, ehi;
+    if (al) { elo = c.rank == NR - 1 ? nvec * EPV : count; ehi = count; }
+    else {
+      const size_t pe = (count + NR - 1) / NR;
+      elo = pe * c.rank < count ? pe * c.rank : count;
+      ehi = elo + pe < count ? elo + pe : count;
+    }
+    for (size_t e = elo + gtid; e < ehi; e += gstride) {
+      T acc = reinterpret_cast<const volatile T*>(c.base[0] + s_a[0])[e];
+      for (int r = 1; r < NR; ++r) acc = Op::template apply<T>(acc, reinterpret_cast<const volatile T*>(c.base[r] + s_a[r])[e]);
+      for (int r = 0; r < NR; ++r) reinterpret_cast<volatile T*>(c.base[r] + s_b[r])[e] = acc;
+    }
+  }
+  sync_end(c);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Allreduce, ring: n-1 reduce-scatter steps then n-1 all-gather steps; each rank only ever loads
 // from its predecessor.  CTA b of rank r depends only on CTA b of rank r-1 (same vector subset on
 // every rank), signalled through ring[b] in the successor's heap.

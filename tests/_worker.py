@@ -19,7 +19,7 @@ from oracle import oracle as O  # noqa: E402
 
 SEED = 0xB2000000
 DTYPES = {"f32": np.float32, "f64": np.float64, "i64": np.int64}
-ALGOS = {"auto": 0, "oneshot": 1, "twoshot": 2, "ring": 3, "nvls": 4}
+ALGOS = {"auto": 0, "oneshot": 1, "twoshot": 2, "ring": 3, "nvls": 4, "smem": 5}
 
 
 def inputs_for(dtype, n, count, salt=0):
@@ -110,7 +110,7 @@ def scenario_collectives(a):
                 for algo in algos:
                     if algo == "nvls" and not nvls:
                         continue
-                    if algo == "ring" and n == 1:
+                    if algo in ("ring", "smem") and n == 1:
                         continue
                     lib.b200mpi_set_algo(L.COLL_ALLREDUCE, ALGOS[algo])
                     used = lib.b200mpi_get_algo(L.COLL_ALLREDUCE, count, O.NP2DT[np.dtype(dt)]) if n > 1 else L.ALGO_TWOSHOT
@@ -177,7 +177,7 @@ def scenario_edge_values(a):
         x = np.roll(x, r * 5)  # different pairings per rank: inf + -inf, 1e38 + 1e38 ...
         ins.append(x.astype(np.float32))
     done = 0
-    for algo in ("oneshot", "twoshot", "ring"):
+    for algo in ("oneshot", "twoshot", "ring", "smem"):
         if algo == "ring" and n == 1:
             continue
         lib.b200mpi_set_algo(L.COLL_ALLREDUCE, ALGOS[algo])
@@ -239,7 +239,7 @@ def scenario_unaligned(a):
         ro = 1 + ((rank + 1) % 2)
         send = big[so:so + count].copy_from_host(ins[rank])
         recv = out[ro:ro + count]
-        for algo in ("oneshot", "twoshot", "ring"):
+        for algo in ("oneshot", "twoshot", "ring", "smem"):
             if algo == "ring" and n == 1:
                 continue
             lib.b200mpi_set_algo(L.COLL_ALLREDUCE, ALGOS[algo])
@@ -466,7 +466,7 @@ def scenario_fullsize(a):
         ins = [O.fill(np.float32, SEED + r, count) for r in range(n)]
         send = mpi.Alloc(count, np.float32).copy_from_host(ins[rank])
         recv = mpi.Alloc(count, np.float32)
-        for algo in ("twoshot", "ring", "oneshot", "nvls"):
+        for algo in ("twoshot", "ring", "oneshot", "nvls", "smem"):
             lib.b200mpi_set_algo(L.COLL_ALLREDUCE, ALGOS[algo])
             used = lib.b200mpi_get_algo(L.COLL_ALLREDUCE, count, L.F32)
             mpi.Allreduce(send, recv)
@@ -529,7 +529,7 @@ def main():
     ap.add_argument("--out", required=True)
     ap.add_argument("--sizes", default="0,1,3,4,5,255,256,257,4096,65537")
     ap.add_argument("--dtypes", default="f32,f64,i64")
-    ap.add_argument("--algos", default="oneshot,twoshot,ring,nvls")
+    ap.add_argument("--algos", default="oneshot,twoshot,ring,nvls,smem")
     ap.add_argument("--kinds", default="heap,host")
     ap.add_argument("--gpu", type=int, default=None)
     ap.add_argument("--what", default="allgather")
