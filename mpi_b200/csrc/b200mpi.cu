@@ -86,6 +86,9 @@ struct Ctx {
   uint32_t* status_dev = nullptr;
   cudaStream_t own_stream = nullptr, stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr; // host-slice pipeline
+  std::vector<cudaEvent_t> pipe_events;
+  size_t pipe_min_bytes = 8u << 20, pipe_chunk_bytes = 16u << 20;
   Mailbox* box = nullptr;
   TagSet sendtags[B200MPI_MAX_RANKS], recvtags[B200MPI_MAX_RANKS];
   std::mutex stream_mu;
@@ -101,6 +104,7 @@ struct Ctx {
   int twoshot_unroll = 1; // 0: 1/2/4 vectors per thread for n = 8/4/2, 1: 2/4/8
   int nvls_unroll = 4;
   int nvls_min_ranks = 4; // below this the fused two-shot moves fewer bytes per link than NVLS
+  size_t own_block_bytes = 1u << 20; // interleave granularity of slice ownership (Owner in kernels.cuh)
 };
 
 static Ctx* g = nullptr;
@@ -222,24 +226,37 @@ static int launch_copy(void* dst, const void* src, size_t bytes, cudaStream_t s)
 // ---------------------------------------------------------------------------------------------
 // kernel dispatch
 // ---------------------------------------------------------------------------------------------
+// log2 of the ownership block, in 16-byte vectors: at most own_block_bytes, at most the per-rank
+// share (so every rank owns something), at least `min_shift`.  Function of (count, n) only.
+static uint32_t own_shift(size_t nvec, int n, uint32_t min_shift) {
+  size_t per = std::max<size_t>((nvec + n - 1) / n, 1);
+  uint32_t sh = 0;
+  while (((size_t)2 << sh) <= per) ++sh;                        // floor(log2(per))
+  uint32_t cap = 0;
+  while (((size_t)32 << cap) <= g->own_block_bytes) ++cap;      // floor(log2(own_block_bytes / 16))
+  sh = std::min(sh, cap);
+  return std::max(sh, min_shift);
+}
+
 template <typename T, typename Op>
 static int launch_allreduce_body_t(int algo, const Comm& c, uint64_t so, uint64_t ro, size_t count, cudaStream_t s) {
   const int n = c.n;
   constexpr int EPV = 16 / sizeof(T);
   const size_t nvec = (count + EPV - 1) / EPV;
   const size_t per = (nvec + n - 1) / n;
+  const uint32_t sh = own_shift(nvec, n, algo == B200MPI_ALGO_TWOSHOT_SMEM ? 8 : 0);
   switch (algo) {
     case B200MPI_ALGO_TWOSHOT: {
       if (g->twoshot_unroll) {
-        if (n == 2) { allreduce_twoshot_kernel<T, Op, 2, 8><<<grid_for(per, 8), kThreads, 0, s>>>(c, so, ro, count); }
-        else if (n == 4) { allreduce_twoshot_kernel<T, Op, 4, 4><<<grid_for(per, 4), kThreads, 0, s>>>(c, so, ro, count); }
-        else if (n == 8) { allreduce_twoshot_kernel<T, Op, 8, 2><<<grid_for(per, 2), kThreads, 0, s>>>(c, so, ro, count); }
-        else { allreduce_twoshot_kernel<T, Op, 0, 2><<<grid_for(per, 2), kThreads, 0, s>>>(c, so, ro, count); }
+        if (n == 2) { allreduce_twoshot_kernel<T, Op, 2, 8><<<grid_for(per, 8), kThreads, 0, s>>>(c, so, ro, count, sh); }
+        else if (n == 4) { allreduce_twoshot_kernel<T, Op, 4, 4><<<grid_for(per, 4), kThreads, 0, s>>>(c, so, ro, count, sh); }
+        else if (n == 8) { allreduce_twoshot_kernel<T, Op, 8, 2><<<grid_for(per, 2), kThreads, 0, s>>>(c, so, ro, count, sh); }
+        else { allreduce_twoshot_kernel<T, Op, 0, 2><<<grid_for(per, 2), kThreads, 0, s>>>(c, so, ro, count, sh); }
       } else {
-        if (n == 2) { allreduce_twoshot_kernel<T, Op, 2, 4><<<grid_for(per, 4), kThreads, 0, s>>>(c, so, ro, count); }
-        else if (n == 4) { allreduce_twoshot_kernel<T, Op, 4, 2><<<grid_for(per, 2), kThreads, 0, s>>>(c, so, ro, count); }
-        else if (n == 8) { allreduce_twoshot_kernel<T, Op, 8, 1><<<grid_for(per, 1), kThreads, 0, s>>>(c, so, ro, count); }
-        else { allreduce_twoshot_kernel<T, Op, 0, 1><<<grid_for(per, 1), kThreads, 0, s>>>(c, so, ro, count); }
+        if (n == 2) { allreduce_twoshot_kernel<T, Op, 2, 4><<<grid_for(per, 4), kThreads, 0, s>>>(c, so, ro, count, sh); }
+        else if (n == 4) { allreduce_twoshot_kernel<T, Op, 4, 2><<<grid_for(per, 2), kThreads, 0, s>>>(c, so, ro, count, sh); }
+        else if (n == 8) { allreduce_twoshot_kernel<T, Op, 8, 1><<<grid_for(per, 1), kThreads, 0, s>>>(c, so, ro, count, sh); }
+        else { allreduce_twoshot_kernel<T, Op, 0, 1><<<grid_for(per, 1), kThreads, 0, s>>>(c, so, ro, count, sh); }
       }
       return launch_check("allreduce_twoshot_kernel");
     }
@@ -259,7 +276,7 @@ static int launch_allreduce_body_t(int algo, const Comm& c, uint64_t so, uint64_
       cudaFuncSetAttribute(allreduce_twoshot_smem_kernel<T, Op, NRV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
       attr_set = true;                                                                                           \
     }                                                                                                            \
-    allreduce_twoshot_smem_kernel<T, Op, NRV><<<blocks, kSmemThreads, smem, s>>>(c, so, ro, count);              \
+    allreduce_twoshot_smem_kernel<T, Op, NRV><<<blocks, kSmemThreads, smem, s>>>(c, so, ro, count, sh);              \
   }
       if (n == 2) B200_SMEM(2)
       else if (n == 4) B200_SMEM(4)
@@ -306,11 +323,12 @@ static int launch_allreduce_nvls_t(uint64_t so, uint64_t ro, size_t count, cudaS
   constexpr int EPV = 16 / sizeof(T);
   const size_t nvec = (count + EPV - 1) / EPV;
   const size_t per = (nvec + c.n - 1) / c.n;
+  const uint32_t sh = own_shift(nvec, c.n, 0);
   switch (g->nvls_unroll) {
-    case 1: allreduce_nvls_kernel<T, Op, 1><<<grid_for(per, 1), kThreads, 0, s>>>(c, so, ro, count); break;
-    case 2: allreduce_nvls_kernel<T, Op, 2><<<grid_for(per, 2), kThreads, 0, s>>>(c, so, ro, count); break;
-    case 8: allreduce_nvls_kernel<T, Op, 8><<<grid_for(per, 8), kThreads, 0, s>>>(c, so, ro, count); break;
-    default: allreduce_nvls_kernel<T, Op, 4><<<grid_for(per, 4), kThreads, 0, s>>>(c, so, ro, count); break;
+    case 1: allreduce_nvls_kernel<T, Op, 1><<<grid_for(per, 1), kThreads, 0, s>>>(c, so, ro, count, sh); break;
+    case 2: allreduce_nvls_kernel<T, Op, 2><<<grid_for(per, 2), kThreads, 0, s>>>(c, so, ro, count, sh); break;
+    case 8: allreduce_nvls_kernel<T, Op, 8><<<grid_for(per, 8), kThreads, 0, s>>>(c, so, ro, count, sh); break;
+    default: allreduce_nvls_kernel<T, Op, 4><<<grid_for(per, 4), kThreads, 0, s>>>(c, so, ro, count, sh); break;
   }
   return launch_check("allreduce_nvls_kernel");
 }
@@ -345,23 +363,41 @@ static int launch_allreduce(int algo, int dtype, int op, uint64_t so, uint64_t r
   return fail(B200MPI_ERR_UNSUPPORTED, "allreduce: unsupported dtype/op (need f32, f64 or i64 with sum/max/min)");
 }
 
+// AUTO for Allreduce.  Thresholds come from the round-1 sweeps on 2/4/8 B200s
+// (profiles/r01/sweep_n*_v1.jsonl): best busbw per (n, size) among the variants.
 static int pick_allreduce(size_t bytes, int dtype, int op) {
+  const int n = g->ctrl.n;
+  const bool pow2 = n == 2 || n == 4 || n == 8;
   int forced = g->algo[B200MPI_COLL_ALLREDUCE];
-  if (forced == B200MPI_ALGO_TWOSHOT_SMEM && !(g->ctrl.n == 2 || g->ctrl.n == 4 || g->ctrl.n == 8)) forced = B200MPI_ALGO_TWOSHOT;
+  if (forced == B200MPI_ALGO_TWOSHOT_SMEM && !pow2) forced = B200MPI_ALGO_TWOSHOT;
   if (forced == B200MPI_ALGO_NVLS && !(g->heap.mc_base && nvls_supports(dtype, op))) forced = 0;
   if (forced) return forced;
+  const bool nvls = g->heap.mc_base && nvls_supports(dtype, op) && n >= g->nvls_min_ranks;
+  const int big = pow2 ? B200MPI_ALGO_TWOSHOT_SMEM : B200MPI_ALGO_TWOSHOT;
+  if (n >= 8) {
+    if (nvls) return (bytes >= (12u << 20) && bytes < (48u << 20)) ? big : B200MPI_ALGO_NVLS;
+    return bytes < (2u << 20) ? B200MPI_ALGO_TWOSHOT : big;
+  }
+  if (n >= 3) {
+    if (nvls && bytes <= (4u << 20)) return B200MPI_ALGO_NVLS;
+    if (!nvls && bytes <= g->oneshot_max_bytes) return B200MPI_ALGO_ONESHOT;
+    return bytes < (2u << 20) ? B200MPI_ALGO_TWOSHOT : big;
+  }
   if (bytes <= g->oneshot_max_bytes) return B200MPI_ALGO_ONESHOT;
-  if (g->heap.mc_base && nvls_supports(dtype, op) && g->ctrl.n >= g->nvls_min_ranks) return B200MPI_ALGO_NVLS;
-  return B200MPI_ALGO_TWOSHOT;
+  return B200MPI_ALGO_TWOSHOT; // n == 2: LDG and TMA-staged two-shot tie (637 vs 636 GB/s at 256 MiB)
 }
 
+// AUTO for Bcast: the switch multicast wins up to a few MiB (one store stream, no second hop);
+// above that the fused pull-slice + push keeps every link busy in both directions
+// (8 GPUs, 256 MiB: 620 GB/s vs 397 NVLS vs 111 everyone-pulls-from-root).
 static int pick_bcast(size_t bytes) {
+  const int n = g->ctrl.n;
   int forced = g->algo[B200MPI_COLL_BCAST];
   if (forced == B200MPI_ALGO_NVLS && !g->heap.mc_base) forced = 0;
   if (forced == B200MPI_ALGO_RING || forced == B200MPI_ALGO_TWOSHOT_SMEM) forced = B200MPI_ALGO_TWOSHOT;
   if (forced) return forced;
-  if (bytes <= g->oneshot_max_bytes || g->ctrl.n == 2) return B200MPI_ALGO_ONESHOT;
-  if (g->heap.mc_base && bytes % 16 == 0 && g->ctrl.n >= g->nvls_min_ranks && getenv("B200MPI_BCAST_NVLS")) return B200MPI_ALGO_NVLS;
+  if (g->heap.mc_base && bytes % 16 == 0 && bytes <= (4u << 20) && n >= 3) return B200MPI_ALGO_NVLS;
+  if (n == 2 || bytes <= (64u << 10)) return B200MPI_ALGO_ONESHOT;
   return B200MPI_ALGO_TWOSHOT;
 }
 
@@ -484,6 +520,48 @@ static int local_copy(void* dst, const void* src, size_t bytes, int memkind, boo
   return finish(async);
 }
 
+// Host slices (what an unmodified Go caller passes): H2D, collective and D2H are pipelined in
+// chunks over three streams so PCIe runs in both directions while the GPUs reduce.  Every rank
+// derives the same chunking from (count, dtype), so the per-chunk collectives line up.
+static int allreduce_host_pipelined(const void* send, void* recv, size_t count, int dtype, int op) {
+  const size_t es = esize(dtype), bytes = count * es;
+  const int n = g->ctrl.n;
+  int rc = ensure_stage(0, bytes);
+  if (rc) return rc;
+  char* stage = (char*)g->heap.base[g->ctrl.rank] + g->stage_off[0];
+  size_t chunk_elems = std::max<size_t>(g->pipe_chunk_bytes / es, 4096) / 4096 * 4096;
+  const size_t nchunks = (count + chunk_elems - 1) / chunk_elems;
+  while (g->pipe_events.size() < 2 * nchunks) {
+    cudaEvent_t e;
+    CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    g->pipe_events.push_back(e);
+  }
+  CUDA_OK(cudaStreamSynchronize(g->stream)); // earlier work may still use the staging block
+  for (size_t k = 0; k < nchunks; ++k) {
+    const size_t lo = k * chunk_elems, len = std::min(chunk_elems, count - lo);
+    cudaEvent_t in = g->pipe_events[2 * k], out = g->pipe_events[2 * k + 1];
+    CUDA_OK(cudaMemcpyAsync(stage + lo * es, (const char*)send + lo * es, len * es, cudaMemcpyHostToDevice, g->h2d_stream));
+    CUDA_OK(cudaEventRecord(in, g->h2d_stream));
+    cudaStream_t tail = g->h2d_stream;
+    if (n > 1) {
+      CUDA_OK(cudaStreamWaitEvent(g->stream, in, 0));
+      const uint64_t off = g->stage_off[0] + lo * es;
+      rc = launch_allreduce(pick_allreduce(len * es, dtype, op), dtype, op, off, off, len, g->stream);
+      if (rc) return rc;
+      CUDA_OK(cudaEventRecord(out, g->stream));
+      tail = g->stream;
+    } else {
+      out = in;
+    }
+    (void)tail;
+    CUDA_OK(cudaStreamWaitEvent(g->d2h_stream, out, 0));
+    CUDA_OK(cudaMemcpyAsync((char*)recv + lo * es, stage + lo * es, len * es, cudaMemcpyDeviceToHost, g->d2h_stream));
+  }
+  CUDA_OK(cudaStreamSynchronize(g->d2h_stream));
+  CUDA_OK(cudaStreamSynchronize(g->stream));
+  return check_status();
+}
+
 static int do_allreduce(const void* send, void* recv, size_t count, int dtype, int op, int memkind, bool async) {
   int rc = need_data_plane();
   if (rc) return rc;
@@ -493,6 +571,7 @@ static int do_allreduce(const void* send, void* recv, size_t count, int dtype, i
   if (count && (!send || !recv)) return fail(B200MPI_ERR_ARG, "allreduce: NULL buffer with count > 0");
   if (memkind != B200MPI_HOST && memkind != B200MPI_DEVICE) return fail(B200MPI_ERR_ARG, "allreduce: bad memkind");
   const size_t bytes = count * es;
+  if (memkind == B200MPI_HOST && !async && bytes >= g->pipe_min_bytes) return allreduce_host_pipelined(send, recv, count, dtype, op);
   if (g->ctrl.n == 1) return local_copy(recv, send, bytes, memkind, async);
   Buf in, out;
   rc = resolve_in(send, bytes, memkind, 0, in);
@@ -840,6 +919,8 @@ int b200mpi_init(const char* addr, const char* alladdr_csv, const char* password
     return bail(B200MPI_ERR_CUDA, "status word allocation failed");
   *g->status_host = 0;
   cudaStreamCreateWithFlags(&g->own_stream, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&g->h2d_stream, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&g->d2h_stream, cudaStreamNonBlocking);
   g->stream = g->own_stream;
   cudaEventCreate(&g->ev0);
   cudaEventCreate(&g->ev1);
@@ -867,6 +948,9 @@ int b200mpi_finalize(void) {
   if (!g->control_only) {
     for (cudaStream_t s : g->stream_pool) cudaStreamDestroy(s);
     if (g->own_stream) cudaStreamDestroy(g->own_stream);
+    if (g->h2d_stream) cudaStreamDestroy(g->h2d_stream);
+    if (g->d2h_stream) cudaStreamDestroy(g->d2h_stream);
+    for (cudaEvent_t e : g->pipe_events) cudaEventDestroy(e);
     if (g->ev0) cudaEventDestroy(g->ev0);
     if (g->ev1) cudaEventDestroy(g->ev1);
     if (g->status_host) cudaFreeHost(g->status_host);
@@ -981,6 +1065,9 @@ int b200mpi_set_param(const char* name, int64_t value) {
   else if (k == "nvls_unroll") g->nvls_unroll = (int)value;
   else if (k == "nvls_min_ranks") g->nvls_min_ranks = (int)value;
   else if (k == "oneshot_max_bytes") g->oneshot_max_bytes = (size_t)value;
+  else if (k == "pipe_min_bytes") g->pipe_min_bytes = (size_t)value;
+  else if (k == "pipe_chunk_bytes") g->pipe_chunk_bytes = (size_t)std::max<int64_t>(value, 65536);
+  else if (k == "own_block_bytes") g->own_block_bytes = (size_t)std::max<int64_t>(value, 4096);
   else if (k == "stage_chunk") g->stage_chunk = (size_t)std::max<int64_t>(value, 4096);
   else return fail(B200MPI_ERR_ARG, "set_param: unknown parameter '" + k + "'");
   return 0;

@@ -332,59 +332,80 @@ allreduce_oneshot_shfl_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size
 }
 
 // ---------------------------------------------------------------------------------------------
-// Allreduce, two-shot fused in one pass: rank j owns slice j; it loads the slice from all n
-// ranks (7 concurrent NVLink read streams + 1 local), reduces in rank order and stores the result
-// into every rank's recv buffer (7 NVLink write streams + 1 local).  Reduce-scatter and
-// all-gather traffic therefore overlap in both link directions and no mid barrier is needed.
-// In-place is safe: slice j of every buffer is read and then written only by rank j.
+// Ownership of the message for the owner-reduces kernels (two-shot, smem two-shot, NVLS).
+// The message is cut into blocks of 2^shift 16-byte vectors; block k belongs to rank k % n, so at
+// any moment all n ranks work inside the same few-MiB window of every heap (fine interleave keeps
+// DRAM pages, GPU TLBs and the switch's multicast tables hot; with one contiguous slice per rank
+// NVLS lost 30% beyond 256 MiB).  The host picks `shift` from (count, n) only, so every rank
+// agrees.  Results do not depend on it: each element is reduced exactly once, in rank order.
+// ---------------------------------------------------------------------------------------------
+struct Owner {
+  size_t nvec;   // whole 16-byte vectors in the message
+  size_t slots;  // upper bound of this rank's local vector slots: (blocks owned) << shift
+  uint32_t shift;
+  int n, rank;
+  __device__ __forceinline__ Owner(size_t nvec_, uint32_t shift_, int n_, int rank_) : nvec(nvec_), shift(shift_), n(n_), rank(rank_) {
+    const size_t nblk = (nvec_ + ((size_t)1 << shift_) - 1) >> shift_;
+    const size_t mine = nblk > (size_t)rank_ ? (nblk - rank_ + n_ - 1) / n_ : 0;
+    slots = mine << shift_;
+  }
+  // local slot -> global vector index (may be >= nvec in the last, partial block)
+  __device__ __forceinline__ size_t global(size_t slot) const {
+    const size_t q = slot >> shift, w = slot & (((size_t)1 << shift) - 1);
+    return ((q * n + rank) << shift) + w;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Allreduce, two-shot fused in one pass: the owner of a vector loads it from all n ranks
+// (7 concurrent NVLink read streams + 1 local), reduces in rank order and stores the result into
+// every rank's recv buffer (7 NVLink write streams + 1 local).  Reduce-scatter and all-gather
+// traffic therefore overlap in both link directions and no mid barrier is needed.
+// In place is safe: a vector is read and then written only by its owner.
 // ---------------------------------------------------------------------------------------------
 template <typename T, typename Op, int NR, int UNROLL>
-__global__ void __launch_bounds__(kThreads, 1)
-allreduce_twoshot_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t count) {
-  __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
-  sync_start(c, send_off, recv_off, s_a, s_b);
+__device__ __forceinline__ void twoshot_body(const Comm& c, const uint64_t* s_a, const uint64_t* s_b, size_t count, uint32_t shift) {
   const int n = NR ? NR : c.n;
   constexpr int R = NR ? NR : kMaxRanks;
   constexpr int EPV = Pack<T>::N;
   const size_t tid = threadIdx.x;
   if (all_aligned16(s_a, s_b, n)) {
     const size_t nvec = count / EPV;
-    const size_t per = (nvec + n - 1) / n;
-    const size_t lo = per * c.rank < nvec ? per * c.rank : nvec;
-    const size_t hi = lo + per < nvec ? lo + per : nvec;
+    const Owner own(nvec, shift, n, c.rank);
     const char* src[R];
     char* dst[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const int q = r < n ? r : 0;
       src[r] = c.base[q] + s_a[q];
-      // stores start at the next rank so the eight ranks do not all hit the same target at once
+      // stores start at the next rank so the ranks do not all hit the same target at once
       const int w = (c.rank + 1 + r) % n;
       dst[r] = c.base[w] + s_b[w];
     }
     const size_t step = (size_t)gridDim.x * blockDim.x * UNROLL;
-    for (size_t i0 = lo + (size_t)blockIdx.x * blockDim.x * UNROLL + tid; i0 < hi; i0 += step) {
+    for (size_t l0 = (size_t)blockIdx.x * blockDim.x * UNROLL + tid; l0 < own.slots; l0 += step) {
       Pack<T> v[UNROLL][R];
+      size_t gi[UNROLL];
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
-        const size_t i = i0 + (size_t)u * blockDim.x;
-        if (i < hi) {
+        const size_t l = l0 + (size_t)u * blockDim.x;
+        gi[u] = l < own.slots ? own.global(l) : nvec;
+        if (gi[u] < nvec) {
 #pragma unroll
           for (int r = 0; r < R; ++r)
-            if (r < n) v[u][r] = ld_pack<T>(src[r] + i * 16);
+            if (r < n) v[u][r] = ld_pack<T>(src[r] + gi[u] * 16);
         }
       }
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
-        const size_t i = i0 + (size_t)u * blockDim.x;
-        if (i < hi) {
+        if (gi[u] < nvec) {
           Pack<T> acc = v[u][0];
 #pragma unroll
           for (int r = 1; r < R; ++r)
             if (r < n) acc = combine<T, Op>(acc, v[u][r]);
 #pragma unroll
           for (int r = 0; r < R; ++r)
-            if (r < n) st_pack<T>(dst[r] + i * 16, acc);
+            if (r < n) st_pack<T>(dst[r] + gi[u] * 16, acc);
         }
       }
     }
@@ -398,7 +419,7 @@ allreduce_twoshot_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t co
       }
     }
   } else {
-    // unaligned buffers: same ownership by element, scalar accesses
+    // unaligned buffers: contiguous ownership by element, scalar accesses
     const size_t per = (count + n - 1) / n;
     const size_t lo = per * c.rank < count ? per * c.rank : count;
     const size_t hi = lo + per < count ? lo + per : count;
@@ -408,6 +429,14 @@ allreduce_twoshot_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t co
       for (int r = 0; r < n; ++r) reinterpret_cast<volatile T*>(c.base[r] + s_b[r])[e] = acc;
     }
   }
+}
+
+template <typename T, typename Op, int NR, int UNROLL>
+__global__ void __launch_bounds__(kThreads, 1)
+allreduce_twoshot_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t count, uint32_t shift) {
+  __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
+  sync_start(c, send_off, recv_off, s_a, s_b);
+  twoshot_body<T, Op, NR, UNROLL>(c, s_a, s_b, count, shift);
   sync_end(c);
 }
 
@@ -460,7 +489,7 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 
 template <typename T, typename Op, int NR>
 __global__ void __launch_bounds__(kSmemThreads, 1)
-allreduce_twoshot_smem_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t count) {
+allreduce_twoshot_smem_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t count, uint32_t shift) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
   __shared__ __align__(8) uint64_t full_bar[kSmemStages], empty_bar[kSmemStages];
@@ -471,11 +500,10 @@ allreduce_twoshot_smem_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size
   const int tid = threadIdx.x;
   const bool al = all_aligned16(s_a, s_b, NR);
   const size_t nvec = al ? count / EPV : 0;
-  const size_t per = (nvec + NR - 1) / NR;
-  const size_t lo = per * c.rank < nvec ? per * c.rank : nvec;
-  const size_t hi = lo + per < nvec ? lo + per : nvec;
-  const size_t slice_bytes = (hi - lo) * 16;
-  const size_t ntiles = (slice_bytes + kSmemChunk - 1) / kSmemChunk;
+  // shift >= 8 (a block is a whole number of 4 KiB tiles); tile t covers local slots [t*256, t*256+256)
+  const Owner own(nvec, shift, NR, c.rank);
+  constexpr size_t kTileVecs = kSmemChunk / 16;
+  const size_t ntiles = own.slots / kTileVecs;
   if (tid == 0) {
     for (int s = 0; s < kSmemStages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -488,12 +516,15 @@ allreduce_twoshot_smem_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size
     // ---- producer warp: one lane drives the TMA loads ----
     if (tid == kSmemConsumers) {
       uint32_t it = 0;
-      for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        if (own.global(t * kTileVecs) >= nvec) continue;
         const int s = it % kSmemStages;
         const uint32_t use = it / kSmemStages;
+        ++it;
         if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1);
-        const size_t off = lo * 16 + t * kSmemChunk;
-        const uint32_t bytes = (uint32_t)((slice_bytes - t * kSmemChunk) < (size_t)kSmemChunk ? (slice_bytes - t * kSmemChunk) : (size_t)kSmemChunk);
+        const size_t g0 = own.global(t * kTileVecs);
+        const size_t off = g0 * 16;
+        const uint32_t bytes = (uint32_t)((nvec - g0) < kTileVecs ? (nvec - g0) * 16 : (size_t)kSmemChunk);
         mbar_expect_tx(&full_bar[s], bytes * NR);
 #pragma unroll
         for (int r = 0; r < NR; ++r)
@@ -502,11 +533,14 @@ allreduce_twoshot_smem_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size
     }
   } else {
     // ---- consumer warps ----
-    uint32_t it = 0;
-    for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    uint32_t nit = 0;
+    for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const size_t g0 = own.global(t * kTileVecs);
+      if (g0 >= nvec) continue;
+      const uint32_t it = nit++;
       const int s = it % kSmemStages;
       const int os = it % kSmemOutStages;
-      const uint32_t bytes = (uint32_t)((slice_bytes - t * kSmemChunk) < (size_t)kSmemChunk ? (slice_bytes - t * kSmemChunk) : (size_t)kSmemChunk);
+      const uint32_t bytes = (uint32_t)((nvec - g0) < kTileVecs ? (nvec - g0) * 16 : (size_t)kSmemChunk);
       mbar_wait(&full_bar[s], (it / kSmemStages) & 1);
       if (it >= (uint32_t)kSmemOutStages) { // the stores that read out_tiles[os] two tiles ago must have drained it
         if (tid == 0) bulk_wait_read<kSmemOutStages - 1>();
@@ -523,7 +557,7 @@ allreduce_twoshot_smem_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size
       asm volatile("bar.sync 1, %0;" ::"n"(kSmemConsumers) : "memory");
       if ((tid & 31) == 0) mbar_arrive(&empty_bar[s]); // this warp is done reading in_tiles[s]
       if (tid == 0) {
-        const size_t off = lo * 16 + t * kSmemChunk;
+        const size_t off = g0 * 16;
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
           const int w = (c.rank + 1 + r) % NR;
@@ -683,7 +717,7 @@ __device__ __forceinline__ void multimem_st16(void* p, uint4 v) {
 
 template <typename T, typename Op, int UNROLL>
 __global__ void __launch_bounds__(kThreads, 1)
-allreduce_nvls_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t count) {
+allreduce_nvls_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t count, uint32_t shift) {
   __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
   sync_start(c, send_off, recv_off, s_a, s_b);
   const int n = c.n;
@@ -691,42 +725,40 @@ allreduce_nvls_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t count
   bool symmetric = ((send_off | recv_off) & 15) == 0;
   for (int r = 0; r < n; ++r) symmetric = symmetric && s_a[r] == send_off && s_b[r] == recv_off;
   const size_t tid = threadIdx.x;
-  const size_t nvec = symmetric ? count / EPV : 0;
   if (symmetric) {
-    const size_t per = (nvec + n - 1) / n;
-    const size_t lo = per * c.rank < nvec ? per * c.rank : nvec;
-    const size_t hi = lo + per < nvec ? lo + per : nvec;
+    const size_t nvec = count / EPV;
+    const Owner own(nvec, shift, n, c.rank);
     const char* src = c.mc + send_off;
     char* dst = c.mc + recv_off;
     const size_t step = (size_t)gridDim.x * blockDim.x * UNROLL;
-    for (size_t i0 = lo + (size_t)blockIdx.x * blockDim.x * UNROLL + tid; i0 < hi; i0 += step) {
+    for (size_t l0 = (size_t)blockIdx.x * blockDim.x * UNROLL + tid; l0 < own.slots; l0 += step) {
       Pack<T> v[UNROLL];
+      size_t gi[UNROLL];
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
-        const size_t i = i0 + (size_t)u * blockDim.x;
-        if (i < hi) v[u] = Multimem<T, Op>::ld_reduce(src + i * 16);
+        const size_t l = l0 + (size_t)u * blockDim.x;
+        gi[u] = l < own.slots ? own.global(l) : nvec;
+        if (gi[u] < nvec) v[u] = Multimem<T, Op>::ld_reduce(src + gi[u] * 16);
       }
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
-        const size_t i = i0 + (size_t)u * blockDim.x;
-        if (i < hi) {
+        if (gi[u] < nvec) {
           union { uint4 u4; Pack<T> k; } x;
           x.k = v[u];
-          multimem_st16(dst + i * 16, x.u4);
+          multimem_st16(dst + gi[u] * 16, x.u4);
         }
       }
     }
-  }
-  // tail elements, or everything when the buffers are not symmetric: last rank, rank order, P2P
-  if (c.rank == n - 1 || !symmetric) {
-    const size_t per = symmetric ? 0 : (count + n - 1) / n;
-    const size_t lo = symmetric ? nvec * EPV : (per * c.rank < count ? per * c.rank : count);
-    const size_t hi = symmetric ? count : (lo + per < count ? lo + per : count);
-    for (size_t e = lo + (size_t)blockIdx.x * blockDim.x + tid; e < hi; e += (size_t)gridDim.x * blockDim.x) {
-      T acc = reinterpret_cast<const volatile T*>(c.base[0] + s_a[0])[e];
-      for (int r = 1; r < n; ++r) acc = Op::template apply<T>(acc, reinterpret_cast<const volatile T*>(c.base[r] + s_a[r])[e]);
-      for (int r = 0; r < n; ++r) reinterpret_cast<volatile T*>(c.base[r] + s_b[r])[e] = acc;
+    if (c.rank == n - 1) { // tail elements: last rank, rank order, P2P
+      for (size_t e = nvec * EPV + (size_t)blockIdx.x * blockDim.x + tid; e < count; e += (size_t)gridDim.x * blockDim.x) {
+        T acc = reinterpret_cast<const volatile T*>(c.base[0] + s_a[0])[e];
+        for (int r = 1; r < n; ++r) acc = Op::template apply<T>(acc, reinterpret_cast<const volatile T*>(c.base[r] + s_a[r])[e]);
+        for (int r = 0; r < n; ++r) reinterpret_cast<volatile T*>(c.base[r] + s_b[r])[e] = acc;
+      }
     }
+  } else {
+    // the multicast address needs the same offsets on every rank; otherwise the P2P two-shot body
+    twoshot_body<T, Op, 0, 1>(c, s_a, s_b, count, shift);
   }
   sync_end(c);
 }

@@ -34,6 +34,8 @@ def main():
     ap.add_argument("--blocks", default="")
     ap.add_argument("--params", default="", help="name=value;name=value passed to b200mpi_set_param")
     ap.add_argument("--tag", default="")
+    ap.add_argument("--param-sets", default="", help="a=1,b=2|a=3,b=4 : the allreduce sweep is repeated for every set")
+    ap.add_argument("--sizes", default="", help="explicit byte sizes, comma separated")
     args, rest = ap.parse_known_args()
     if "RANK" in os.environ:
         rank, world, local, addr, addrs = bench.world_from_env(None)
@@ -98,6 +100,9 @@ def main():
     while b <= args.max_bytes:
         sizes.append(b)
         b *= 2
+    if args.sizes:
+        sizes = [int(x) for x in args.sizes.split(",")]
+    param_sets = [dict((kv.split("=")[0], int(kv.split("=")[1])) for kv in ps.split(",") if kv) for ps in args.param_sets.split("|") if ps] or [{}]
     colls = args.colls.split(",")
     maxc = args.max_bytes // 4
     blocks_list = [int(x) for x in args.blocks.split(",") if x] or [0]
@@ -106,28 +111,33 @@ def main():
         send = mpi.Alloc(maxc, np.float32).copy_from_host(np.full(maxc, rank + 1, dtype=np.float32))
         recv = mpi.Alloc(maxc, np.float32)
         want = np.float32(n * (n + 1) // 2)
-        for algo in args.algos.split(","):
-            if algo == "nvls" and not nvls:
-                continue
-            if n == 1 and algo != "twoshot":
-                continue
-            lib.b200mpi_set_algo(L.COLL_ALLREDUCE, ALGOS[algo])
-            for nb in blocks_list:
-                lib.b200mpi_set_max_blocks(nb)
-                for S in sizes:
-                    if algo == "oneshot" and S > (8 << 20):
-                        continue
-                    cnt = S // 4
-                    it, wm = iters_for(S)
-                    t = timed(lambda: lib.b200mpi_allreduce_async(send.ptr, recv.ptr, cnt, L.F32, L.SUM), it, wm)
-                    t0 = time.perf_counter()
-                    for _ in range(5):
-                        lib.b200mpi_allreduce(send.ptr, recv.ptr, cnt, L.F32, L.SUM, L.DEVICE)
-                    tc = maxr((time.perf_counter() - t0) / 5)
-                    probe = np.concatenate([recv[:min(cnt, 64)].to_host(), recv[max(cnt - 64, 0):cnt].to_host(), recv[cnt // 2:cnt // 2 + 1].to_host()])
-                    ok = bool(np.all(probe == want))
-                    emit({"coll": "allreduce", "dtype": "f32", "algo": algo, "bytes": S, "t_us": t * 1e6, "t_call_us": tc * 1e6,
-                          "algbw_gbs": S / t / 1e9, "busbw_gbs": S / t / 1e9 * (2 * (n - 1) / n if n > 1 else 1), "ok": ok, "max_blocks": nb})
+        for ps in param_sets:
+          for k, v in ps.items():
+            params[k] = v
+            if lib.b200mpi_set_param(k.encode(), int(v)):
+                raise RuntimeError(L.last_error())
+          for algo in args.algos.split(","):
+              if algo == "nvls" and not nvls:
+                  continue
+              if n == 1 and algo != "twoshot":
+                  continue
+              lib.b200mpi_set_algo(L.COLL_ALLREDUCE, ALGOS[algo])
+              for nb in blocks_list:
+                  lib.b200mpi_set_max_blocks(nb)
+                  for S in sizes:
+                      if algo == "oneshot" and S > (8 << 20):
+                          continue
+                      cnt = S // 4
+                      it, wm = iters_for(S)
+                      t = timed(lambda: lib.b200mpi_allreduce_async(send.ptr, recv.ptr, cnt, L.F32, L.SUM), it, wm)
+                      t0 = time.perf_counter()
+                      for _ in range(5):
+                          lib.b200mpi_allreduce(send.ptr, recv.ptr, cnt, L.F32, L.SUM, L.DEVICE)
+                      tc = maxr((time.perf_counter() - t0) / 5)
+                      probe = np.concatenate([recv[:min(cnt, 64)].to_host(), recv[max(cnt - 64, 0):cnt].to_host(), recv[cnt // 2:cnt // 2 + 1].to_host()])
+                      ok = bool(np.all(probe == want))
+                      emit({"coll": "allreduce", "dtype": "f32", "algo": algo, "bytes": S, "t_us": t * 1e6, "t_call_us": tc * 1e6,
+                            "algbw_gbs": S / t / 1e9, "busbw_gbs": S / t / 1e9 * (2 * (n - 1) / n if n > 1 else 1), "ok": ok, "max_blocks": nb, "pset": dict(ps)})
         lib.b200mpi_set_algo(L.COLL_ALLREDUCE, 0)
         lib.b200mpi_set_max_blocks(0)
         send.free()
