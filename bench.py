@@ -105,6 +105,18 @@ def measured_peaks():
         return {"hbm_gbs": HBM_FALLBACK_GBS}, "fallback"
 
 
+def measured_traffic(n, nbytes, kernel):
+    """dram read+write bytes per launch from the committed ncu captures (profiles/traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            for e in json.load(f)["entries"]:
+                if e["n"] == n and e["bytes"] == nbytes and e["kernel"] == kernel:
+                    return e["traffic_bytes"], e["source"]
+    except Exception:  # noqa: BLE001
+        pass
+    return None, None
+
+
 def reference_arm(n, count, dtype, steps, warmup):
     """Times oracle/ref_tcp.c (restated reference) with n ranks (threads) on this host."""
     from oracle import oracle as O
@@ -253,9 +265,14 @@ def main():
                 "frac": value / NVLINK_NOMINAL_GBS, "frac_of_measured_peer_copy": value / NVLINK_MEASURED_GBS,
                 "traffic": None, "peak_source": "nominal NVLink 5 per direction per GPU; measured peer copy %.0f GB/s" % NVLINK_MEASURED_GBS,
                 "kernel": "allreduce_%s_kernel" % L.ALGO_NAMES.get(algo_used, "?"),
+                "nvls_link_bytes_per_launch": (1.0 + 1.0 / n) * S if L.ALGO_NAMES.get(algo_used) == "nvls" else None,
                 "algorithmic_bytes_per_launch": 2.0 * (n - 1) / n * S,
                 "hbm": {"achieved": hbm_bytes / t_step / 1e9, "peak": hbm_peak, "frac": hbm_bytes / t_step / 1e9 / hbm_peak, "peak_source": peak_kind}}
 
+    traffic, tsrc = measured_traffic(n, S, roof["kernel"])
+    if traffic is not None:
+        roof["traffic"] = traffic
+        roof["traffic_source"] = tsrc
     info = (ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_int())
     lib.b200mpi_heap_info(ctypes.byref(info[0]), ctypes.byref(info[1]), ctypes.byref(info[2]))
 

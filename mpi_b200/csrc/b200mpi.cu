@@ -102,7 +102,8 @@ struct Ctx {
   std::atomic<int64_t> launches{0};
   size_t oneshot_max_bytes = 256u << 10;
   int twoshot_unroll = 1; // 0: 1/2/4 vectors per thread for n = 8/4/2, 1: 2/4/8
-  int nvls_unroll = 4;
+  int nvls_unroll = 2;      // 8 GPUs, 256 MiB: unroll 2 x 64 CTAs 810 GB/s, 4 x 148 CTAs 780 (profiles/r01/sweep_n8_nvls_blocks_unroll_v2.jsonl)
+  int nvls_max_blocks = 64; // fewer requests in flight suit the switch reduction better
   int nvls_min_ranks = 4; // below this the fused two-shot moves fewer bytes per link than NVLS
   size_t own_block_bytes = 1u << 20; // interleave granularity of slice ownership (Owner in kernels.cuh)
 };
@@ -324,11 +325,14 @@ static int launch_allreduce_nvls_t(uint64_t so, uint64_t ro, size_t count, cudaS
   const size_t nvec = (count + EPV - 1) / EPV;
   const size_t per = (nvec + c.n - 1) / c.n;
   const uint32_t sh = own_shift(nvec, c.n, 0);
-  switch (g->nvls_unroll) {
-    case 1: allreduce_nvls_kernel<T, Op, 1><<<grid_for(per, 1), kThreads, 0, s>>>(c, so, ro, count, sh); break;
-    case 2: allreduce_nvls_kernel<T, Op, 2><<<grid_for(per, 2), kThreads, 0, s>>>(c, so, ro, count, sh); break;
-    case 8: allreduce_nvls_kernel<T, Op, 8><<<grid_for(per, 8), kThreads, 0, s>>>(c, so, ro, count, sh); break;
-    default: allreduce_nvls_kernel<T, Op, 4><<<grid_for(per, 4), kThreads, 0, s>>>(c, so, ro, count, sh); break;
+  const int u = g->nvls_unroll;
+  int blocks = grid_for(per, u == 1 || u == 2 || u == 8 ? u : 4);
+  if (g->max_blocks == 0 && blocks > g->nvls_max_blocks) blocks = g->nvls_max_blocks;
+  switch (u) {
+    case 1: allreduce_nvls_kernel<T, Op, 1><<<blocks, kThreads, 0, s>>>(c, so, ro, count, sh); break;
+    case 2: allreduce_nvls_kernel<T, Op, 2><<<blocks, kThreads, 0, s>>>(c, so, ro, count, sh); break;
+    case 8: allreduce_nvls_kernel<T, Op, 8><<<blocks, kThreads, 0, s>>>(c, so, ro, count, sh); break;
+    default: allreduce_nvls_kernel<T, Op, 4><<<blocks, kThreads, 0, s>>>(c, so, ro, count, sh); break;
   }
   return launch_check("allreduce_nvls_kernel");
 }
@@ -375,7 +379,7 @@ static int pick_allreduce(size_t bytes, int dtype, int op) {
   const bool nvls = g->heap.mc_base && nvls_supports(dtype, op) && n >= g->nvls_min_ranks;
   const int big = pow2 ? B200MPI_ALGO_TWOSHOT_SMEM : B200MPI_ALGO_TWOSHOT;
   if (n >= 8) {
-    if (nvls) return (bytes >= (12u << 20) && bytes < (48u << 20)) ? big : B200MPI_ALGO_NVLS;
+    if (nvls) return B200MPI_ALGO_NVLS; // fastest at every size from 1 KiB (15 us) to 1 GiB (834 GB/s)
     return bytes < (2u << 20) ? B200MPI_ALGO_TWOSHOT : big;
   }
   if (n >= 3) {
@@ -1064,6 +1068,7 @@ int b200mpi_set_param(const char* name, int64_t value) {
   if (k == "twoshot_unroll") g->twoshot_unroll = value ? 1 : 0;
   else if (k == "nvls_unroll") g->nvls_unroll = (int)value;
   else if (k == "nvls_min_ranks") g->nvls_min_ranks = (int)value;
+  else if (k == "nvls_max_blocks") g->nvls_max_blocks = (int)std::max<int64_t>(1, value);
   else if (k == "oneshot_max_bytes") g->oneshot_max_bytes = (size_t)value;
   else if (k == "pipe_min_bytes") g->pipe_min_bytes = (size_t)value;
   else if (k == "pipe_chunk_bytes") g->pipe_chunk_bytes = (size_t)std::max<int64_t>(value, 65536);
