@@ -104,6 +104,7 @@ struct Ctx {
   int twoshot_unroll = 1; // 0: 1/2/4 vectors per thread for n = 8/4/2, 1: 2/4/8
   int nvls_unroll = 2;      // 8 GPUs, 256 MiB: unroll 2 x 64 CTAs 810 GB/s, 4 x 148 CTAs 780 (profiles/r01/sweep_n8_nvls_blocks_unroll_v2.jsonl)
   int nvls_max_blocks = 64; // fewer requests in flight suit the switch reduction better
+  int copy_variant = 5; // 16 vectors in flight per thread, 256 threads: best of 8 launch shapes at 256 MiB and 1 GiB
   int nvls_min_ranks = 4; // below this the fused two-shot moves fewer bytes per link than NVLS
   size_t own_block_bytes = 1u << 20; // interleave granularity of slice ownership (Owner in kernels.cuh)
 };
@@ -219,8 +220,25 @@ static int launch_check(const char* what) {
 // dst <- src on `s` with the library's own copy kernel (local HBM or peer mapping).
 static int launch_copy(void* dst, const void* src, size_t bytes, cudaStream_t s) {
   if (bytes == 0) return 0;
-  int blocks = grid_for((bytes + 15) / 16, 4);
-  copy_bytes_kernel<4><<<blocks, kThreads, 0, s>>>((unsigned char*)dst, (const unsigned char*)src, bytes);
+  unsigned char* d = (unsigned char*)dst;
+  const unsigned char* c = (const unsigned char*)src;
+  const size_t nvec = (bytes + 15) / 16;
+  const int sms = g->sm_count;
+  auto grid = [&](int threads, int unroll, int per_sm) {
+    size_t want = (nvec + (size_t)threads * unroll - 1) / ((size_t)threads * unroll);
+    size_t cap = g->max_blocks > 0 ? (size_t)g->max_blocks : (size_t)sms * per_sm;
+    return (int)std::max<size_t>(1, std::min(want, cap));
+  };
+  switch (g->copy_variant) { // launch shapes for the HBM-bound local copy; see profiles/r01/SUMMARY.md
+    case 1: copy_bytes_kernel<8, 512, 1><<<grid(512, 8, 1), 512, 0, s>>>(d, c, bytes); break;
+    case 2: copy_bytes_kernel<4, 256, 2><<<grid(256, 4, 2), 256, 0, s>>>(d, c, bytes); break;
+    case 3: copy_bytes_kernel<8, 256, 2><<<grid(256, 8, 2), 256, 0, s>>>(d, c, bytes); break;
+    case 4: copy_bytes_kernel<4, 1024, 1><<<grid(1024, 4, 1), 1024, 0, s>>>(d, c, bytes); break;
+    case 5: copy_bytes_kernel<16, 256, 1><<<grid(256, 16, 1), 256, 0, s>>>(d, c, bytes); break;
+    case 6: copy_bytes_kernel<2, 1024, 2><<<grid(1024, 2, 2), 1024, 0, s>>>(d, c, bytes); break;
+    case 7: copy_bytes_kernel<4, 512, 2><<<grid(512, 4, 2), 512, 0, s>>>(d, c, bytes); break;
+    default: copy_bytes_kernel<4, 512, 1><<<grid(512, 4, 1), 512, 0, s>>>(d, c, bytes); break;
+  }
   return launch_check("copy_bytes_kernel");
 }
 
@@ -546,18 +564,15 @@ static int allreduce_host_pipelined(const void* send, void* recv, size_t count, 
     cudaEvent_t in = g->pipe_events[2 * k], out = g->pipe_events[2 * k + 1];
     CUDA_OK(cudaMemcpyAsync(stage + lo * es, (const char*)send + lo * es, len * es, cudaMemcpyHostToDevice, g->h2d_stream));
     CUDA_OK(cudaEventRecord(in, g->h2d_stream));
-    cudaStream_t tail = g->h2d_stream;
     if (n > 1) {
       CUDA_OK(cudaStreamWaitEvent(g->stream, in, 0));
       const uint64_t off = g->stage_off[0] + lo * es;
       rc = launch_allreduce(pick_allreduce(len * es, dtype, op), dtype, op, off, off, len, g->stream);
       if (rc) return rc;
       CUDA_OK(cudaEventRecord(out, g->stream));
-      tail = g->stream;
     } else {
-      out = in;
+      out = in; // world of one: the D2H only waits for its own H2D
     }
-    (void)tail;
     CUDA_OK(cudaStreamWaitEvent(g->d2h_stream, out, 0));
     CUDA_OK(cudaMemcpyAsync((char*)recv + lo * es, stage + lo * es, len * es, cudaMemcpyDeviceToHost, g->d2h_stream));
   }
@@ -1068,6 +1083,7 @@ int b200mpi_set_param(const char* name, int64_t value) {
   if (k == "twoshot_unroll") g->twoshot_unroll = value ? 1 : 0;
   else if (k == "nvls_unroll") g->nvls_unroll = (int)value;
   else if (k == "nvls_min_ranks") g->nvls_min_ranks = (int)value;
+  else if (k == "copy_variant") g->copy_variant = (int)value;
   else if (k == "nvls_max_blocks") g->nvls_max_blocks = (int)std::max<int64_t>(1, value);
   else if (k == "oneshot_max_bytes") g->oneshot_max_bytes = (size_t)value;
   else if (k == "pipe_min_bytes") g->pipe_min_bytes = (size_t)value;

@@ -968,8 +968,8 @@ bcast_nvls_kernel(Comm c, uint64_t buf_off, size_t bytes, int root) {
 // Point-to-point and local copies: dst <- src, `bytes` bytes, any alignment.  src may be a peer
 // mapping (receiver pulls the sender's posted region over NVLink).
 // ---------------------------------------------------------------------------------------------
-template <int UNROLL>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int UNROLL, int THREADS = kThreads, int MINB = 1>
+__global__ void __launch_bounds__(THREADS, MINB)
 copy_bytes_kernel(unsigned char* __restrict__ dst, const unsigned char* __restrict__ src, size_t bytes) {
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;

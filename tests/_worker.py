@@ -493,6 +493,48 @@ def scenario_fullsize(a):
     return {"checked": done}
 
 
+def scenario_stream(a):
+    """Caller-provided stream (b200mpi_set_stream) + enqueue-only calls + the event stopwatch."""
+    import ctypes
+    import torch
+    lib = L.load()
+    rank, n = mpi.Rank(), mpi.Size()
+    dev = lib.b200mpi_device()
+    torch.cuda.set_device(dev)
+    st = torch.cuda.Stream(device=dev)
+    own = ctypes.c_void_p()
+    assert lib.b200mpi_get_stream(ctypes.byref(own)) == 0 and own.value
+    assert lib.b200mpi_set_stream(ctypes.c_void_p(st.cuda_stream)) == 0
+    cur = ctypes.c_void_p()
+    lib.b200mpi_get_stream(ctypes.byref(cur))
+    assert cur.value == st.cuda_stream
+    count = 1 << 18
+    ins = [O.fill(np.float32, SEED + r, count) for r in range(n)]
+    send = mpi.Alloc(count, np.float32).copy_from_host(ins[rank])
+    recv = mpi.Alloc(count, np.float32)
+    gath = mpi.Alloc(count * n, np.float32)
+    l0 = lib.b200mpi_launch_count()
+    assert lib.b200mpi_timer_start() == 0
+    assert lib.b200mpi_allreduce_async(send.ptr, recv.ptr, count, L.F32, L.SUM) == 0, L.last_error()
+    assert lib.b200mpi_allgather_async(send.ptr, gath.ptr, count, L.F32) == 0, L.last_error()
+    assert lib.b200mpi_bcast_async(send.ptr, count, L.F32, 0) == 0, L.last_error()
+    ms = ctypes.c_float()
+    assert lib.b200mpi_timer_stop(ctypes.byref(ms)) == 0 and ms.value > 0
+    st.synchronize()
+    assert lib.b200mpi_stream_sync() == 0
+    assert lib.b200mpi_launch_count() - l0 == (3 if n > 1 else 2)  # world of 1: bcast is a no-op
+    used = lib.b200mpi_get_algo(L.COLL_ALLREDUCE, count, L.F32) if n > 1 else L.ALGO_TWOSHOT
+    want, order = expect_allreduce(ins, O.SUM, used, n, count, np.float32)
+    check_equal(recv.to_host(), want, "allreduce on caller stream", exact=order != O.ORDER_F64, ins=ins)
+    check_equal(gath.to_host(), O.allgather(ins), "allgather on caller stream")
+    check_equal(send.to_host(), ins[0], "bcast on caller stream")
+    assert lib.b200mpi_set_stream(None) == 0
+    lib.b200mpi_get_stream(ctypes.byref(cur))
+    assert cur.value == own.value
+    mpi.Barrier()
+    return {"checked": 3}
+
+
 def scenario_smoke(a):
     rank, n = mpi.Rank(), mpi.Size()
     x = O.fill(np.float32, SEED + rank, 1 << 12)

@@ -79,6 +79,11 @@ def test_concurrent_tags_and_duplicate_tag():
     world(2, "tags")
 
 
+@pytest.mark.parametrize("n", [1, 2])
+def test_caller_stream_async_calls_and_timer(n):
+    world(n, "stream")
+
+
 def test_full_size_points():
     """BASELINE.json sizes: Allgather int64 1 Mi per rank x 8 ranks bit-exact; Allreduce f32 at 16 Mi
     elements (64 MiB) with every algorithm; bounce 1 MiB float64 is covered above."""

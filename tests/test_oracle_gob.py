@@ -15,6 +15,38 @@ def _put(fn, v):
     return bytes(buf[:n]).hex()
 
 
+def _golden():
+    import json, os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "gob_doc_vectors.json")) as f:
+        return json.load(f)
+
+
+def test_golden_fixture_vectors():
+    """Every entry of tests/golden/gob_doc_vectors.json (transcribed from the gob documentation)."""
+    g = _golden()
+    for v, want in g["uint"].items():
+        assert _put("gob_put_uint", int(v)) == want
+    for v, want in g["int"].items():
+        assert _put("gob_put_int", int(v)) == want
+    for v, want in g["float"].items():
+        assert _put("gob_put_float", float(v)) == want
+    names = (ctypes.c_char_p * 2)(b"X", b"Y")
+    ids = (ctypes.c_int * 2)(2, 2)
+    buf = (ctypes.c_uint8 * 128)()
+    n = O.lib().gob_put_struct_typedef(buf, b"Point", 65, 2, names, ids)
+    assert bytes(buf[:n]).hex() == g["point_type_descriptor"]
+    # the value message: length, type id 65, field 0 = 22, field 1 = 33, end of struct
+    val = bytes.fromhex(g["point_value_22_33"])
+    assert val == bytes([7]) + bytes.fromhex(_put("gob_put_int", 65)) + b"\x01" + bytes.fromhex(_put("gob_put_int", 22)) + b"\x01" + bytes.fromhex(_put("gob_put_int", 33)) + b"\x00"
+    import json, os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "splitmix64.json")) as f:
+        sm = json.load(f)
+    for i, h in enumerate(sm["seed0"]):
+        assert O.lib().oracle_splitmix64(0, i) == int(h, 16)
+    for i, h in enumerate(sm["seed_b2000000"]):
+        assert O.lib().oracle_splitmix64(0xB2000000, i) == int(h, 16)
+
+
 def test_documented_scalar_encodings():
     assert _put("gob_put_uint", 0) == "00"
     assert _put("gob_put_uint", 7) == "07"
