@@ -82,6 +82,7 @@ struct Ctx {
   bool shared_device = false; // several ranks on one GPU (functional-test mode)
   Comm comm = {};
   uint32_t epoch = 1;
+  uint64_t cur_sig = 0; // signature of the collective being launched (checked by sync_start on every rank)
   uint32_t* status_host = nullptr; // mapped pinned
   uint32_t* status_dev = nullptr;
   cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -197,6 +198,7 @@ static int grid_for(size_t units_per_rank, int unroll) {
 static Comm next_comm(uint32_t mids = 0) {
   Comm c = g->comm;
   c.epoch = g->epoch;
+  c.sig = g->cur_sig;
   c.end_epoch = g->epoch + 1 + mids;
   g->epoch += 2 + mids;
   return c;
@@ -204,10 +206,18 @@ static Comm next_comm(uint32_t mids = 0) {
 
 static int check_status() {
   if (g->status_host && *(volatile uint32_t*)g->status_host) {
+    const uint32_t st = *(volatile uint32_t*)g->status_host;
     *(volatile uint32_t*)g->status_host = 0;
+    if (st == 2u) return fail(B200MPI_ERR_PEER, "mismatched collective: ranks disagree on the call (collective, count, dtype, op, root or algorithm); buffers were left untouched");
     return fail(B200MPI_ERR_TIMEOUT, "device-side watchdog: a peer did not reach the collective in time");
   }
   return 0;
+}
+
+// (count, collective, dtype, op/root, algorithm) folded into one word; equal on every rank of a
+// well-formed call.  coll: 0 allreduce, 1 bcast, 2 allgather, 3 barrier.
+static uint64_t make_sig(int coll, int dtype, int extra, int algo, size_t count) {
+  return ((uint64_t)count << 16) ^ ((uint64_t)(coll & 3) << 14) ^ ((uint64_t)(dtype & 3) << 12) ^ ((uint64_t)(extra & 15) << 8) ^ ((uint64_t)(algo & 15) << 4) ^ 0x5u;
 }
 
 static int launch_check(const char* what) {
@@ -361,6 +371,7 @@ static bool nvls_supports(int dtype, int op) {
 }
 
 static int launch_allreduce(int algo, int dtype, int op, uint64_t so, uint64_t ro, size_t count, cudaStream_t s) {
+  g->cur_sig = make_sig(0, dtype, op, algo, count);
   if (algo == B200MPI_ALGO_NVLS) {
     if (dtype == B200MPI_F32 && op == B200MPI_SUM) return launch_allreduce_nvls_t<float, OpSum>(so, ro, count, s);
     if (dtype == B200MPI_F64 && op == B200MPI_SUM) return launch_allreduce_nvls_t<double, OpSum>(so, ro, count, s);
@@ -621,6 +632,7 @@ static int do_bcast(void* buf, size_t count, int dtype, int root, int memkind, b
   else rc = resolve_out(buf, bytes, memkind, 0, b);
   if (rc) return rc;
   const int algo = pick_bcast(bytes);
+  g->cur_sig = make_sig(1, dtype, root, algo, count);
   Comm c = next_comm();
   if (algo == B200MPI_ALGO_NVLS) {
     bcast_nvls_kernel<4><<<grid_for(bytes / 16 + 1, 4), kThreads, 0, g->stream>>>(c, b.off, bytes, root);
@@ -650,6 +662,7 @@ static int do_allgather(const void* send, void* recv, size_t count, int dtype, i
   if (inplace && !out.staged) { in.off = out.off + (size_t)g->ctrl.rank * bytes; }
   else { rc = resolve_in(send, bytes, memkind, 0, in); if (rc) return rc; }
   const int algo = pick_allgather(bytes);
+  g->cur_sig = make_sig(2, dtype, 0, algo, count);
   Comm c = next_comm();
   rc = launch_units(algo == B200MPI_ALGO_RING ? 1 : 0, c, in.off, out.off, bytes, 0, 0, g->stream);
   if (rc) return rc;
@@ -1055,6 +1068,7 @@ int b200mpi_barrier(void) {
     return rc ? fail(rc, err) : 0;
   }
   if (g->ctrl.n == 1) return finish(false);
+  g->cur_sig = make_sig(3, 0, 0, 0, 0);
   Comm c = next_comm();
   barrier_kernel<<<1, 32, 0, g->stream>>>(c);
   int rc = launch_check("barrier_kernel");

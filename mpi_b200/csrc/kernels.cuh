@@ -49,6 +49,7 @@ struct Comm {
   int rank, n;
   uint32_t epoch;            // start barrier value
   uint32_t end_epoch;        // end barrier value (epoch + 1 + number of reserved mid barriers)
+  uint64_t sig;              // what this rank thinks the call is: (count, collective, dtype, op, algorithm)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -98,21 +99,37 @@ __device__ __forceinline__ Slot* slot_of(const Comm& c, int owner, int block, in
   return reinterpret_cast<Slot*>(c.base[owner]) + (size_t)block * kMaxRanks + src;
 }
 
-// Per-CTA barrier #1: announce {a,b} to every rank, wait for everyone's, publish them in smem.
-__device__ __forceinline__ void sync_start(const Comm& c, uint64_t a, uint64_t b, uint64_t* s_a,
+// Per-CTA barrier #1: announce {a,b,sig} to every rank, wait for everyone's, publish the offsets
+// in smem.  Returns false (and raises status 2) when a peer's signature differs from ours -- ranks
+// called different collectives / counts / types -- so the body is skipped instead of touching
+// memory out of bounds; sync_end still runs, nobody hangs, the host reports B200MPI_ERR_PEER.
+__device__ __forceinline__ bool sync_start(const Comm& c, uint64_t a, uint64_t b, uint64_t* s_a,
                                            uint64_t* s_b) {
+  __shared__ int s_bad;
   const int t = threadIdx.x;
+  if (t == 0) s_bad = 0;
+  __syncthreads();
   if (t < c.n) {
     Slot* theirs = slot_of(c, t, blockIdx.x, c.rank);
     st_relaxed_sys_u64(&theirs->a, a);
     st_relaxed_sys_u64(&theirs->b, b);
+    st_relaxed_sys_u64(&theirs->c, c.sig);
     st_release_sys(&theirs->flag, c.epoch);
     Slot* mine = slot_of(c, c.rank, blockIdx.x, t);
     wait_flag(&mine->flag, c.epoch, c);
     s_a[t] = ld_relaxed_sys_u64(&mine->a);
     s_b[t] = ld_relaxed_sys_u64(&mine->b);
+    if (ld_relaxed_sys_u64(&mine->c) != c.sig) s_bad = 1;
   }
   __syncthreads();
+  if (s_bad) {
+    if (t == 0) {
+      *(volatile uint32_t*)c.status = 2u;
+      __threadfence_system();
+    }
+    return false;
+  }
+  return true;
 }
 
 // Per-CTA barrier #2: all of this CTA's stores (local, peer and multicast) are released to every
@@ -230,7 +247,11 @@ template <typename T, typename Op, int NR>
 __global__ void __launch_bounds__(kThreads, 1)
 allreduce_oneshot_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t count) {
   __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
-  sync_start(c, send_off, recv_off, s_a, s_b);
+  const bool call_ok = sync_start(c, send_off, recv_off, s_a, s_b);
+  if (!call_ok) { // ranks disagree about this call: touch nothing, leave through the end barrier
+    sync_end(c);
+    return;
+  }
   const int n = NR ? NR : c.n;
   const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t gstride = (size_t)gridDim.x * blockDim.x;
@@ -278,7 +299,11 @@ __global__ void __launch_bounds__(kThreads, 1)
 allreduce_oneshot_shfl_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t count) {
   __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
   __shared__ const char* s_src[kMaxRanks];
-  sync_start(c, send_off, recv_off, s_a, s_b);
+  const bool call_ok = sync_start(c, send_off, recv_off, s_a, s_b);
+  if (!call_ok) { // ranks disagree about this call: touch nothing, leave through the end barrier
+    sync_end(c);
+    return;
+  }
   if (threadIdx.x < NR) s_src[threadIdx.x] = c.base[threadIdx.x] + s_a[threadIdx.x];
   __syncthreads();
   constexpr int EPV = Pack<T>::N;
@@ -435,7 +460,11 @@ template <typename T, typename Op, int NR, int UNROLL>
 __global__ void __launch_bounds__(kThreads, 1)
 allreduce_twoshot_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t count, uint32_t shift) {
   __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
-  sync_start(c, send_off, recv_off, s_a, s_b);
+  const bool call_ok = sync_start(c, send_off, recv_off, s_a, s_b);
+  if (!call_ok) { // ranks disagree about this call: touch nothing, leave through the end barrier
+    sync_end(c);
+    return;
+  }
   twoshot_body<T, Op, NR, UNROLL>(c, s_a, s_b, count, shift);
   sync_end(c);
 }
@@ -495,7 +524,11 @@ allreduce_twoshot_smem_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size
   __shared__ __align__(8) uint64_t full_bar[kSmemStages], empty_bar[kSmemStages];
   unsigned char* in_tiles = smem_raw;                                         // [stage][rank][chunk]
   unsigned char* out_tiles = smem_raw + (size_t)kSmemStages * NR * kSmemChunk; // [ostage][chunk]
-  sync_start(c, send_off, recv_off, s_a, s_b);
+  const bool call_ok = sync_start(c, send_off, recv_off, s_a, s_b);
+  if (!call_ok) { // ranks disagree about this call: touch nothing, leave through the end barrier
+    sync_end(c);
+    return;
+  }
   constexpr int EPV = Pack<T>::N;
   const int tid = threadIdx.x;
   const bool al = all_aligned16(s_a, s_b, NR);
@@ -601,7 +634,11 @@ template <typename T, typename Op>
 __global__ void __launch_bounds__(kThreads, 1)
 allreduce_ring_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t count) {
   __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
-  sync_start(c, send_off, recv_off, s_a, s_b);
+  const bool call_ok = sync_start(c, send_off, recv_off, s_a, s_b);
+  if (!call_ok) { // ranks disagree about this call: touch nothing, leave through the end barrier
+    sync_end(c);
+    return;
+  }
   const int n = c.n, r = c.rank;
   const int prev = (r + n - 1) % n, next = (r + 1) % n;
   constexpr int EPV = Pack<T>::N;
@@ -719,7 +756,11 @@ template <typename T, typename Op, int UNROLL>
 __global__ void __launch_bounds__(kThreads, 1)
 allreduce_nvls_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t count, uint32_t shift) {
   __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
-  sync_start(c, send_off, recv_off, s_a, s_b);
+  const bool call_ok = sync_start(c, send_off, recv_off, s_a, s_b);
+  if (!call_ok) { // ranks disagree about this call: touch nothing, leave through the end barrier
+    sync_end(c);
+    return;
+  }
   const int n = c.n;
   constexpr int EPV = Pack<T>::N;
   bool symmetric = ((send_off | recv_off) & 15) == 0;
@@ -821,7 +862,11 @@ template <typename U, int UNROLL>
 __global__ void __launch_bounds__(kThreads, 1)
 allgather_push_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t bytes_per_rank) {
   __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
-  sync_start(c, send_off, recv_off, s_a, s_b);
+  const bool call_ok = sync_start(c, send_off, recv_off, s_a, s_b);
+  if (!call_ok) { // ranks disagree about this call: touch nothing, leave through the end barrier
+    sync_end(c);
+    return;
+  }
   if (sizeof(U) == 1 || all_aligned_to(s_a, s_b, c.n, sizeof(U))) allgather_push_body<U, UNROLL>(c, s_a, s_b, bytes_per_rank);
   else allgather_push_body<unsigned char, 1>(c, s_a, s_b, bytes_per_rank);
   sync_end(c);
@@ -862,7 +907,11 @@ template <typename U>
 __global__ void __launch_bounds__(kThreads, 1)
 allgather_ring_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t bytes_per_rank) {
   __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
-  sync_start(c, send_off, recv_off, s_a, s_b);
+  const bool call_ok = sync_start(c, send_off, recv_off, s_a, s_b);
+  if (!call_ok) { // ranks disagree about this call: touch nothing, leave through the end barrier
+    sync_end(c);
+    return;
+  }
   if (sizeof(U) == 1 || all_aligned_to(s_a, s_b, c.n, sizeof(U))) allgather_ring_body<U>(c, s_a, s_b, bytes_per_rank);
   else allgather_ring_body<unsigned char>(c, s_a, s_b, bytes_per_rank);
   sync_end(c);
@@ -921,7 +970,11 @@ template <typename U, int UNROLL>
 __global__ void __launch_bounds__(kThreads, 1)
 bcast_kernel(Comm c, uint64_t buf_off, size_t bytes, int root, int mode) {
   __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
-  sync_start(c, buf_off, buf_off, s_a, s_b);
+  const bool call_ok = sync_start(c, buf_off, buf_off, s_a, s_b);
+  if (!call_ok) { // ranks disagree about this call: touch nothing, leave through the end barrier
+    sync_end(c);
+    return;
+  }
   if (sizeof(U) == 1 || all_aligned_to(s_a, s_b, c.n, sizeof(U))) bcast_body<U, UNROLL>(c, s_a, bytes, root, mode);
   else bcast_body<unsigned char, 1>(c, s_a, bytes, root, mode);
   sync_end(c);
@@ -932,7 +985,11 @@ template <int UNROLL>
 __global__ void __launch_bounds__(kThreads, 1)
 bcast_nvls_kernel(Comm c, uint64_t buf_off, size_t bytes, int root) {
   __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
-  sync_start(c, buf_off, buf_off, s_a, s_b);
+  const bool call_ok = sync_start(c, buf_off, buf_off, s_a, s_b);
+  if (!call_ok) { // ranks disagree about this call: touch nothing, leave through the end barrier
+    sync_end(c);
+    return;
+  }
   const int n = c.n;
   bool symmetric = (buf_off & 15) == 0 && (bytes & 15) == 0;
   for (int r = 0; r < n; ++r) symmetric = symmetric && s_a[r] == buf_off;
@@ -1004,7 +1061,7 @@ copy_bytes_kernel(unsigned char* __restrict__ dst, const unsigned char* __restri
 // A device-wide rendezvous with nothing in between (b200mpi_barrier).
 __global__ void barrier_kernel(Comm c) {
   __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
-  sync_start(c, 0, 0, s_a, s_b);
+  (void)sync_start(c, 0, 0, s_a, s_b);
   sync_end(c);
 }
 

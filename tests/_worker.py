@@ -535,6 +535,38 @@ def scenario_stream(a):
     return {"checked": 3}
 
 
+def scenario_mismatch(a):
+    """Ranks that disagree on count / dtype / collective get B200MPI_ERR_PEER, not a hang and not
+    an out-of-bounds access; the library keeps working afterwards."""
+    rank, n = mpi.Rank(), mpi.Size()
+    lib = L.load()
+    done = 0
+    # different counts
+    cnt = 1000 if rank == 0 else 999
+    x = mpi.Alloc(1000, np.float32).copy_from_host(np.ones(1000, dtype=np.float32))
+    y = mpi.Alloc(1000, np.float32).copy_from_host(np.full(1000, -5, dtype=np.float32))
+    rc = lib.b200mpi_allreduce(x.ptr, y.ptr, cnt, L.F32, L.SUM, L.DEVICE)
+    assert rc == L.ERR_PEER, (rc, L.last_error())
+    check_equal(y.to_host(), np.full(1000, -5, dtype=np.float32), "recv untouched after a mismatched call")
+    done += 1
+    # different dtypes (same byte size)
+    rc = lib.b200mpi_allreduce(x.ptr, y.ptr, 500, L.F64 if rank == 0 else L.I64, L.SUM, L.DEVICE)
+    assert rc == L.ERR_PEER, (rc, L.last_error())
+    done += 1
+    # different collectives
+    if rank == 0:
+        rc = lib.b200mpi_bcast(x.ptr, 1000, L.F32, 0, L.DEVICE)
+    else:
+        rc = lib.b200mpi_allgather(x.ptr, y.ptr, 1000 // n, L.F32, L.DEVICE)
+    assert rc == L.ERR_PEER, (rc, L.last_error())
+    done += 1
+    # and the world still works
+    mpi.Allreduce(x, y)
+    check_equal(y.to_host(), np.full(1000, n, dtype=np.float32), "allreduce after mismatches")
+    mpi.Barrier()
+    return {"checked": done + 1}
+
+
 def scenario_smoke(a):
     rank, n = mpi.Rank(), mpi.Size()
     x = O.fill(np.float32, SEED + rank, 1 << 12)

@@ -84,6 +84,11 @@ def test_caller_stream_async_calls_and_timer(n):
     world(n, "stream")
 
 
+def test_mismatched_collectives_are_reported_not_hung():
+    world(2, "mismatch")
+    world(4, "mismatch")
+
+
 def test_full_size_points():
     """BASELINE.json sizes: Allgather int64 1 Mi per rank x 8 ranks bit-exact; Allreduce f32 at 16 Mi
     elements (64 MiB) with every algorithm; bounce 1 MiB float64 is covered above."""
