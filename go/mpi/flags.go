@@ -47,13 +47,13 @@ func init() {
 		str         *string
 		def         string
 	}{
-		{"mpi-addr", "address of the local running process", &FlagAddr, ""},
-		{"mpi-protocol", "communication protocol to use", &FlagProtocol, "tcp"},
-		{"mpi-password", "value to use for salting the mpi connection", &FlagPassword, ""},
+		{"mpi-addr", "this rank's own address (host:port or :port); its position in the sorted -mpi-alladdr list is the rank", &FlagAddr, ""},
+		{"mpi-protocol", "kept for command-line compatibility; the control plane always speaks tcp", &FlagProtocol, "tcp"},
+		{"mpi-password", "shared secret every rank must present during the Init handshake", &FlagPassword, ""},
 	} {
 		flag.StringVar(f.str, f.name, f.def, f.usage)
 	}
-	flag.Var(&FlagAllAddrs, "mpi-alladdr", "addresses of all of the processes as comma separated values")
-	flag.Var(&FlagInitTimeout, "mpi-inittimeout", "duration to wait before timeout in init")
+	flag.Var(&FlagAllAddrs, "mpi-alladdr", "every rank's address, comma separated; may be given several times")
+	flag.Var(&FlagInitTimeout, "mpi-inittimeout", "give up Init after this long (Go duration syntax); 0 waits forever")
 	flag.IntVar(&FlagGpu, "mpi-gpu", -1, "CUDA device ordinal for this rank (-1: rank modulo device count)")
 }
