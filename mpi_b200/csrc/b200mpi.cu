@@ -878,6 +878,13 @@ int b200mpi_init(const char* addr, const char* alladdr_csv, const char* password
   if (const char* w = getenv("B200MPI_ONESHOT_MAX")) g->oneshot_max_bytes = strtoull(w, nullptr, 0);
   auto bail = [&](int code, const std::string& m) {
     // tell nobody: peers notice through their own control-plane errors / timeouts
+    if (g->box) munmap(g->box, sizeof(Mailbox));
+    if (g->status_host) cudaFreeHost(g->status_host);
+    for (cudaStream_t st : {g->own_stream, g->h2d_stream, g->d2h_stream})
+      if (st) cudaStreamDestroy(st);
+    if (g->ev0) cudaEventDestroy(g->ev0);
+    if (g->ev1) cudaEventDestroy(g->ev1);
+    if (g->drv.MemUnmap) g->heap.destroy(g->drv); // no-op when the heap was never created
     g->ctrl.shutdown();
     delete g;
     g = nullptr;

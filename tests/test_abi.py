@@ -79,6 +79,22 @@ def test_init_without_a_device_fails_loudly():
     assert "CODE -10" in out and "no CPU fallback" in out, out
 
 
+@pytest.mark.skipif(_has_gpu(), reason="box has a GPU")
+def test_failed_init_leaves_the_library_reusable():
+    code = (
+        "from mpi_b200 import _lib as L\n"
+        "lib = L.load()\n"
+        "rc1 = lib.b200mpi_init(b'', b'', b'', 0, -1)\n"      # no device -> fails, state must be reset
+        "r1 = (lib.b200mpi_rank(), lib.b200mpi_size())\n"
+        "rc2 = lib.b200mpi_init(b'', b'', b'', 0, -2)\n"      # control plane only -> works
+        "r2 = (lib.b200mpi_rank(), lib.b200mpi_size())\n"
+        "rc3 = lib.b200mpi_init(b'', b'', b'', 0, -2)\n"      # Init twice -> error
+        "rc4 = lib.b200mpi_finalize()\n"
+        "print(rc1, r1, rc2, r2, rc3, rc4, lib.b200mpi_rank())\n")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, env=dict(os.environ, PYTHONPATH=ROOT)).stdout
+    assert out.split() == ["-10", "(-1,", "0)", "0", "(0,", "1)", "-1", "0", "-1"], out
+
+
 def test_product_does_not_import_the_oracle():
     """oracle/ is test infrastructure: nothing under mpi_b200/ may reference it."""
     for dirpath, _, files in os.walk(os.path.join(ROOT, "mpi_b200")):
