@@ -441,22 +441,24 @@ static int pick_allgather(size_t) {
 }
 
 // which: 0 allgather push, 1 allgather ring, 2 bcast (extra = root, mode 0 one-shot / 1 two-shot)
+// The grid is a function of the byte count only: ranks may instantiate different access widths
+// (their offsets differ in alignment) but must launch the same number of CTAs, because the
+// barriers pair CTAs by blockIdx.
 template <typename U>
 static void launch_units_u(int which, const Comm& c, uint64_t a, uint64_t b, size_t bytes, int extra, int mode, cudaStream_t s) {
   constexpr int UNROLL = 4;
-  const size_t units = bytes / sizeof(U);
-  if (which == 0) allgather_push_kernel<U, UNROLL><<<grid_for(units, UNROLL), kThreads, 0, s>>>(c, a, b, bytes);
-  else if (which == 1) allgather_ring_kernel<U><<<grid_for(units, UNROLL), kThreads, 0, s>>>(c, a, b, bytes);
+  const size_t vecs = bytes / 16 + 1;
+  if (which == 0) allgather_push_kernel<U, UNROLL><<<grid_for(vecs, UNROLL), kThreads, 0, s>>>(c, a, b, bytes);
+  else if (which == 1) allgather_ring_kernel<U><<<grid_for(vecs, UNROLL), kThreads, 0, s>>>(c, a, b, bytes);
   else {
-    const size_t work = mode == 1 ? units / (size_t)(c.n - 1) + 1 : units;
+    const size_t work = mode == 1 ? vecs / (size_t)(c.n - 1) + 1 : vecs;
     bcast_kernel<U, UNROLL><<<grid_for(work, UNROLL), kThreads, 0, s>>>(c, a, bytes, extra, mode);
   }
 }
 static int launch_units(int which, const Comm& c, uint64_t a, uint64_t b, size_t bytes, int extra, int mode, cudaStream_t s) {
-  // The widest access unit that divides the size.  Offsets of other ranks are unknown here, so
-  // the host only looks at its own; a rank whose offsets are less aligned than its peers' would
-  // fault, hence heap blocks are 512-byte aligned and user offsets must keep 16-byte alignment
-  // for the wide path (checked below against this rank's offsets only).
+  // The widest access unit that divides the size and THIS rank's offsets.  Peers may be aligned
+  // differently: after sync_start every rank knows all offsets and drops to the byte-wide body if
+  // some peer's are narrower than its own unit (kernels.cuh: all_aligned_to).
   const uint64_t m = a | b | bytes;
   if ((m & 15) == 0) launch_units_u<uint4>(which, c, a, b, bytes, extra, mode, s);
   else if ((m & 7) == 0) launch_units_u<unsigned long long>(which, c, a, b, bytes, extra, mode, s);

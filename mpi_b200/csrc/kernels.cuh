@@ -934,11 +934,15 @@ __device__ __forceinline__ void bcast_body(const Comm& c, const uint64_t* s_a, s
   U* dst[kMaxRanks];
   dst[0] = reinterpret_cast<U*>(c.base[c.rank] + s_a[c.rank]);
   if (mode == 1) {
+    // slices are cut in bytes on 16-byte granules so that ranks running different access widths
+    // (their offsets differ in alignment) still cover the buffer exactly once
     const int m = n - 1;
     const int k = c.rank < root ? c.rank : c.rank - 1;
-    const size_t per = (units + m - 1) / m;
-    lo = per * k < units ? per * k : units;
-    hi = lo + per < units ? lo + per : units;
+    const size_t per_b = ((bytes + 15) / 16 + m - 1) / m * 16;
+    const size_t lo_b = per_b * k < bytes ? per_b * k : bytes;
+    const size_t hi_b = lo_b + per_b < bytes ? lo_b + per_b : bytes;
+    lo = lo_b / sizeof(U);
+    hi = hi_b / sizeof(U);
     for (int j = 1; j < n; ++j) { // other non-roots, starting after me
       const int w = (c.rank + j) % n;
       if (w == root) continue;

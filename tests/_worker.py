@@ -266,6 +266,31 @@ def scenario_unaligned(a):
             check_equal(b.to_host(), ins[1 % n], "unaligned bcast %s %s" % (dn, algo))
             done += 1
         lib.b200mpi_set_algo(L.COLL_BCAST, 0)
+        # mixed access widths: the size is a multiple of 16 but the offsets are 8/16/24 bytes
+        # depending on the rank, and the message spans many CTAs
+        if dt != np.float32:
+            big_n = 65536
+            wide = mpi.Alloc(big_n * (n + 1) + 16, dt)
+            wsrc = mpi.Alloc(big_n + 16, dt)
+            wins = inputs_for(dt, n, big_n, salt=9)
+            ws = wsrc[so:so + big_n].copy_from_host(wins[rank])
+            wr = wide[2:2 + big_n * n]  # 16-byte aligned everywhere: the send offset alone decides each rank's width
+            for algo in ("auto", "ring"):
+                lib.b200mpi_set_algo(L.COLL_ALLGATHER, ALGOS[algo])
+                mpi.Allgather(ws, wr)
+                check_equal(wr.to_host(), O.allgather(wins), "mixed-width allgather %s %s" % (dn, algo))
+                done += 1
+            lib.b200mpi_set_algo(L.COLL_ALLGATHER, 0)
+            for algo in ("oneshot", "twoshot"):
+                lib.b200mpi_set_algo(L.COLL_BCAST, ALGOS[algo])
+                root = (n - 1) % n
+                wb = wsrc[so:so + big_n].copy_from_host(wins[root] if rank == root else np.zeros(big_n, dtype=dt))
+                mpi.Bcast(wb, root)
+                check_equal(wb.to_host(), wins[root], "mixed-width bcast %s %s" % (dn, algo))
+                done += 1
+            lib.b200mpi_set_algo(L.COLL_BCAST, 0)
+            wide.free()
+            wsrc.free()
         # bytes: odd length, odd offset
         raw = np.frombuffer(O.fill(np.int64, SEED + rank, 200).tobytes(), dtype=np.uint8)[:1501]
         rb = np.zeros(1501 * n, dtype=np.uint8)
