@@ -65,3 +65,14 @@ def test_bounce_cpp():
     assert "Number of nodes =  2" in out.stdout
     assert "Average float64 trip time in us between node 0 and 1" in out.stdout
     assert "message not the same" not in out.stderr
+
+
+def test_cpp_facade_host_logic():
+    """mpi.hpp on a CPU-only box: flags, durations, Register-once, pre-Init answers."""
+    import tempfile
+    exe = os.path.join(tempfile.mkdtemp(prefix="b200mpi-facade-"), "facade_test")
+    lib = os.path.join(ROOT, "mpi_b200", "lib")
+    subprocess.check_call([os.environ.get("CXX", "g++"), "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "tests", "cpp", "facade_test.cpp"),
+                           "-L" + lib, "-lb200mpi", "-Wl,-rpath," + lib, "-pthread"])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "facade ok" in out.stdout, out.stdout + out.stderr
