@@ -61,7 +61,8 @@ typedef enum {
                                bcast: pull-slice-from-root + push to all, one fused pass */
   B200MPI_ALGO_RING = 3,    /* allreduce/allgather: 2(n-1) / (n-1) neighbour steps */
   B200MPI_ALGO_NVLS = 4,    /* multimem.ld_reduce / multimem.st through the NVSwitch */
-  B200MPI_ALGO_TWOSHOT_SMEM = 5 /* allreduce two-shot with cp.async.bulk shared-memory staging */
+  B200MPI_ALGO_TWOSHOT_SMEM = 5, /* allreduce two-shot with cp.async.bulk shared-memory staging */
+  B200MPI_ALGO_LL = 6        /* allreduce <= 32 KiB: flag-in-data cells, no barrier (experimental) */
 } b200mpi_algo;
 
 typedef enum {

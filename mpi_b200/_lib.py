@@ -14,8 +14,8 @@ U8, I64, F32, F64 = 0, 1, 2, 3
 SUM, MAX, MIN = 0, 1, 2
 HOST, DEVICE = 0, 1
 COLL_ALLREDUCE, COLL_BCAST, COLL_ALLGATHER = 0, 1, 2
-ALGO_AUTO, ALGO_ONESHOT, ALGO_TWOSHOT, ALGO_RING, ALGO_NVLS, ALGO_TWOSHOT_SMEM = 0, 1, 2, 3, 4, 5
-ALGO_NAMES = {0: "auto", 1: "oneshot", 2: "twoshot", 3: "ring", 4: "nvls", 5: "twoshot_smem"}
+ALGO_AUTO, ALGO_ONESHOT, ALGO_TWOSHOT, ALGO_RING, ALGO_NVLS, ALGO_TWOSHOT_SMEM, ALGO_LL = 0, 1, 2, 3, 4, 5, 6
+ALGO_NAMES = {0: "auto", 1: "oneshot", 2: "twoshot", 3: "ring", 4: "nvls", 5: "twoshot_smem", 6: "ll"}
 
 OK = 0
 ERR_ARG, ERR_NOT_INIT, ERR_BOOTSTRAP, ERR_PASSWORD, ERR_TIMEOUT, ERR_TAG_EXISTS = -1, -2, -3, -4, -5, -6

@@ -105,6 +105,8 @@ struct Ctx {
   int twoshot_unroll = 1; // 0: 1/2/4 vectors per thread for n = 8/4/2, 1: 2/4/8
   int nvls_unroll = 2;      // 8 GPUs, 256 MiB: unroll 2 x 64 CTAs 810 GB/s, 4 x 148 CTAs 780 (profiles/r01/sweep_n8_nvls_blocks_unroll_v2.jsonl)
   int nvls_max_blocks = 64; // fewer requests in flight suit the switch reduction better
+  size_t ll_max_bytes = 0; // > 0 enables the experimental LL allreduce for messages up to this size (<= 32 KiB)
+  uint32_t ll_seq = 0;
   int copy_variant = 5; // 16 vectors in flight per thread, 256 threads: best of 8 launch shapes at 256 MiB and 1 GiB
   int nvls_min_ranks = 4; // below this the fused two-shot moves fewer bytes per link than NVLS
   size_t own_block_bytes = 1u << 20; // interleave granularity of slice ownership (Owner in kernels.cuh)
@@ -404,7 +406,9 @@ static int pick_allreduce(size_t bytes, int dtype, int op) {
   int forced = g->algo[B200MPI_COLL_ALLREDUCE];
   if (forced == B200MPI_ALGO_TWOSHOT_SMEM && !pow2) forced = B200MPI_ALGO_TWOSHOT;
   if (forced == B200MPI_ALGO_NVLS && !(g->heap.mc_base && nvls_supports(dtype, op))) forced = 0;
+  if (forced == B200MPI_ALGO_LL && bytes > kLLCells * 8) forced = 0;
   if (forced) return forced;
+  if (g->ll_max_bytes && bytes <= g->ll_max_bytes) return B200MPI_ALGO_LL;
   const bool nvls = g->heap.mc_base && nvls_supports(dtype, op) && n >= g->nvls_min_ranks;
   const int big = pow2 ? B200MPI_ALGO_TWOSHOT_SMEM : B200MPI_ALGO_TWOSHOT;
   if (n >= 8) {
@@ -555,6 +559,33 @@ static int local_copy(void* dst, const void* src, size_t bytes, int memkind, boo
   return finish(async);
 }
 
+// EXPERIMENTAL (never run on hardware): barrier-free LL allreduce for <= 32 KiB, any local device pointers.
+template <typename T, typename Op>
+static int launch_ll_t(const void* send, void* recv, size_t count, cudaStream_t s) {
+  Comm c = g->comm;
+  const uint32_t seq = ++g->ll_seq;
+  const size_t ncell = (count * sizeof(T) + 7) / 8;
+  const int blocks = (int)std::max<size_t>(1, std::min<size_t>((ncell + 255) / 256, 16));
+  allreduce_ll_kernel<T, Op><<<blocks, 256, 0, s>>>(c, (const T*)send, (T*)recv, count, seq);
+  return launch_check("allreduce_ll_kernel");
+}
+static int launch_ll(int dtype, int op, const void* send, void* recv, size_t count, cudaStream_t s) {
+#define B200_LL(T)                                                            \
+  switch (op) {                                                               \
+    case B200MPI_SUM: return launch_ll_t<T, OpSum>(send, recv, count, s);     \
+    case B200MPI_MAX: return launch_ll_t<T, OpMax>(send, recv, count, s);     \
+    case B200MPI_MIN: return launch_ll_t<T, OpMin>(send, recv, count, s);     \
+  }                                                                           \
+  break;
+  switch (dtype) {
+    case B200MPI_F32: B200_LL(float)
+    case B200MPI_F64: B200_LL(double)
+    case B200MPI_I64: B200_LL(long long)
+  }
+#undef B200_LL
+  return fail(B200MPI_ERR_UNSUPPORTED, "allreduce(LL): unsupported dtype/op");
+}
+
 // Host slices (what an unmodified Go caller passes): H2D, collective and D2H are pipelined in
 // chunks over three streams so PCIe runs in both directions while the GPUs reduce.  Every rank
 // derives the same chunking from (count, dtype), so the per-chunk collectives line up.
@@ -605,6 +636,21 @@ static int do_allreduce(const void* send, void* recv, size_t count, int dtype, i
   const size_t bytes = count * es;
   if (memkind == B200MPI_HOST && !async && bytes >= g->pipe_min_bytes) return allreduce_host_pipelined(send, recv, count, dtype, op);
   if (g->ctrl.n == 1) return local_copy(recv, send, bytes, memkind, async);
+  if (pick_allreduce(bytes, dtype, op) == B200MPI_ALGO_LL) {
+    // any local device pointer works (peers never read it); host slices go through the staging block
+    if (memkind == B200MPI_DEVICE) {
+      rc = launch_ll(dtype, op, send, recv, count, g->stream);
+      return rc ? rc : finish(async);
+    }
+    Buf b;
+    rc = resolve_in(send, bytes, memkind, 0, b);
+    if (rc) return rc;
+    char* p = (char*)g->heap.base[g->ctrl.rank] + b.off;
+    rc = launch_ll(dtype, op, p, p, count, g->stream);
+    if (rc) return rc;
+    rc = copy_out(recv, bytes, memkind, b);
+    return rc ? rc : finish(async);
+  }
   Buf in, out;
   rc = resolve_in(send, bytes, memkind, 0, in);
   if (rc) return rc;
@@ -1087,7 +1133,7 @@ int b200mpi_barrier(void) {
 
 int b200mpi_set_algo(int coll, int algo) {
   if (!g || !g->initialised) return fail(B200MPI_ERR_NOT_INIT, "mpi: Init has not been called");
-  if (coll < 0 || coll > 2 || algo < 0 || algo > B200MPI_ALGO_TWOSHOT_SMEM) return fail(B200MPI_ERR_ARG, "set_algo: bad collective or algorithm id");
+  if (coll < 0 || coll > 2 || algo < 0 || algo > B200MPI_ALGO_LL) return fail(B200MPI_ERR_ARG, "set_algo: bad collective or algorithm id");
   g->algo[coll] = algo;
   return 0;
 }
@@ -1107,6 +1153,7 @@ int b200mpi_set_param(const char* name, int64_t value) {
   else if (k == "nvls_unroll") g->nvls_unroll = (int)value;
   else if (k == "nvls_min_ranks") g->nvls_min_ranks = (int)value;
   else if (k == "copy_variant") g->copy_variant = (int)value;
+  else if (k == "ll_max_bytes") g->ll_max_bytes = (size_t)std::min<int64_t>(std::max<int64_t>(value, 0), (int64_t)(kLLCells * 8));
   else if (k == "nvls_max_blocks") g->nvls_max_blocks = (int)std::max<int64_t>(1, value);
   else if (k == "oneshot_max_bytes") g->oneshot_max_bytes = (size_t)value;
   else if (k == "pipe_min_bytes") g->pipe_min_bytes = (size_t)value;

@@ -29,6 +29,8 @@ constexpr int kMaxRanks = 8;
 constexpr int kMaxBlocks = 592;            // 148 SMs x 4
 constexpr size_t kCtrlBytes = 2u << 20;    // control region at the start of every heap
 constexpr size_t kRingFlagsOff = 512u << 10;
+constexpr size_t kLLOff = 1u << 20;          // LL cells: [parity 2][src rank 8][kLLCells] x 16 B = 1 MiB
+constexpr size_t kLLCells = 4096;            // 8 payload bytes per cell -> 32 KiB per call
 constexpr int kThreads = 512;
 
 struct __align__(32) Slot {
@@ -1059,6 +1061,98 @@ copy_bytes_kernel(unsigned char* __restrict__ dst, const unsigned char* __restri
     for (size_t i = head + nvec * 16 + tid; i < bytes; i += stride) dst[i] = src[i];
   } else {
     for (size_t i = tid; i < bytes; i += stride) dst[i] = src[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Allreduce, LL (low latency) -- EXPERIMENTAL, written in round 1 after the GPU budget was spent:
+// compiles, has never run on hardware, off unless "ll_max_bytes" > 0.
+// One kernel, no barrier at all.  Every rank pushes its whole (<= 32 KiB) message into a private
+// lane of every peer's heap as 16-byte cells {data32, seq, data32, seq} (the NCCL "LL" layout: each
+// 8-byte half carries its own flag, so only 8-byte store atomicity is assumed), then reduces its
+// own lane set in rank order, spinning per cell until both flags equal this call's sequence number.
+// Lanes are double buffered by seq parity: a peer can only be one call ahead, because finishing
+// call k+1 needs this rank's k+1 cells, which are sent after this rank finished reading call k.
+// Peers never read this rank's send buffer, so there is no end barrier and in place is free; send
+// and recv may be any local device pointers.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4* ll_lane(const Comm& c, int owner, uint32_t parity, int src) {
+  return reinterpret_cast<uint4*>(c.base[owner] + kLLOff) + ((size_t)parity * kMaxRanks + src) * kLLCells;
+}
+__device__ __forceinline__ void st_cell(uint4* p, uint4 v) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_cell(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+template <typename T> struct LLCodec; // 8 payload bytes <-> elements
+template <> struct LLCodec<float> {
+  static constexpr int EPC = 2;
+  __device__ __forceinline__ static void pack(const float* e, uint32_t& w0, uint32_t& w1) { w0 = __float_as_uint(e[0]); w1 = __float_as_uint(e[1]); }
+  __device__ __forceinline__ static void unpack(uint32_t w0, uint32_t w1, float* e) { e[0] = __uint_as_float(w0); e[1] = __uint_as_float(w1); }
+};
+template <> struct LLCodec<double> {
+  static constexpr int EPC = 1;
+  __device__ __forceinline__ static void pack(const double* e, uint32_t& w0, uint32_t& w1) { unsigned long long b = (unsigned long long)__double_as_longlong(e[0]); w0 = (uint32_t)b; w1 = (uint32_t)(b >> 32); }
+  __device__ __forceinline__ static void unpack(uint32_t w0, uint32_t w1, double* e) { e[0] = __longlong_as_double((long long)(((unsigned long long)w1 << 32) | w0)); }
+};
+template <> struct LLCodec<long long> {
+  static constexpr int EPC = 1;
+  __device__ __forceinline__ static void pack(const long long* e, uint32_t& w0, uint32_t& w1) { unsigned long long b = (unsigned long long)e[0]; w0 = (uint32_t)b; w1 = (uint32_t)(b >> 32); }
+  __device__ __forceinline__ static void unpack(uint32_t w0, uint32_t w1, long long* e) { e[0] = (long long)(((unsigned long long)w1 << 32) | w0); }
+};
+
+template <typename T, typename Op>
+__global__ void __launch_bounds__(256, 1)
+allreduce_ll_kernel(Comm c, const T* __restrict__ send, T* recv, size_t count, uint32_t seq) {
+  constexpr int EPC = LLCodec<T>::EPC;
+  const size_t ncell = (count + EPC - 1) / EPC;
+  const uint32_t parity = seq & 1u;
+  const int n = c.n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncell; i += (size_t)gridDim.x * blockDim.x) {
+    T mine[EPC];
+#pragma unroll
+    for (int k = 0; k < EPC; ++k) mine[k] = i * EPC + k < count ? send[i * EPC + k] : T(0);
+    uint32_t w0, w1;
+    LLCodec<T>::pack(mine, w0, w1);
+    const uint4 cell = make_uint4(w0, seq, w1, seq);
+    for (int j = 1; j < n; ++j) { // push to every peer, starting after this rank
+      const int r = (c.rank + j) % n;
+      st_cell(ll_lane(c, r, parity, c.rank) + i, cell);
+    }
+    T acc[EPC];
+    for (int r = 0; r < n; ++r) { // rank order
+      T v[EPC];
+      if (r == c.rank) {
+#pragma unroll
+        for (int k = 0; k < EPC; ++k) v[k] = mine[k];
+      } else {
+        const uint4* src = ll_lane(c, c.rank, parity, r) + i;
+        uint4 got = ld_cell(src);
+        unsigned long long t0 = 0;
+        uint32_t it = 0;
+        while (got.y != seq || got.w != seq) {
+          if ((++it & 0xfffu) == 0) {
+            const unsigned long long now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            else if (c.timeout_ns && now - t0 > c.timeout_ns) {
+              *(volatile uint32_t*)c.status = 1u;
+              __threadfence_system();
+              break;
+            }
+          }
+          got = ld_cell(src);
+        }
+        LLCodec<T>::unpack(got.x, got.z, v);
+      }
+#pragma unroll
+      for (int k = 0; k < EPC; ++k) acc[k] = r == 0 ? v[k] : Op::template apply<T>(acc[k], v[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < EPC; ++k)
+      if (i * EPC + k < count) recv[i * EPC + k] = acc[k];
   }
 }
 

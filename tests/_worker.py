@@ -19,7 +19,7 @@ from oracle import oracle as O  # noqa: E402
 
 SEED = 0xB2000000
 DTYPES = {"f32": np.float32, "f64": np.float64, "i64": np.int64}
-ALGOS = {"auto": 0, "oneshot": 1, "twoshot": 2, "ring": 3, "nvls": 4, "smem": 5}
+ALGOS = {"auto": 0, "oneshot": 1, "twoshot": 2, "ring": 3, "nvls": 4, "smem": 5, "ll": 6}
 
 
 def inputs_for(dtype, n, count, salt=0):

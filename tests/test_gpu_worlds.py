@@ -89,6 +89,12 @@ def test_mismatched_collectives_are_reported_not_hung():
     world(4, "mismatch")
 
 
+@pytest.mark.parametrize("n", [2, 4])
+def test_ll_allreduce_experimental(n):
+    """Barrier-free LL allreduce (<= 32 KiB, off by default): rank-order results, bit-exact."""
+    world(n, "collectives", "--algos", "ll", "--sizes", "0,1,2,3,257,4097,8192", "--kinds", "heap,host")
+
+
 def test_full_size_points():
     """BASELINE.json sizes: Allgather int64 1 Mi per rank x 8 ranks bit-exact; Allreduce f32 at 16 Mi
     elements (64 MiB) with every algorithm; bounce 1 MiB float64 is covered above."""
