@@ -1065,8 +1065,10 @@ copy_bytes_kernel(unsigned char* __restrict__ dst, const unsigned char* __restri
 }
 
 // ---------------------------------------------------------------------------------------------
-// Allreduce, LL (low latency) -- EXPERIMENTAL, written in round 1 after the GPU budget was spent:
-// compiles, has never run on hardware, off unless "ll_max_bytes" > 0.
+// Allreduce, LL (low latency) -- EXPERIMENTAL, written at the end of round 1: bit-exact against the
+// oracle in worlds of 2 and 4 ranks sharing one B200 (tests/test_gpu_worlds.py::test_ll_...), but
+// its latency over NVLink has not been measured yet, so it is off unless "ll_max_bytes" > 0 or
+// the algorithm is forced.
 // One kernel, no barrier at all.  Every rank pushes its whole (<= 32 KiB) message into a private
 // lane of every peer's heap as 16-byte cells {data32, seq, data32, seq} (the NCCL "LL" layout: each
 // 8-byte half carries its own flag, so only 8-byte store atomicity is assumed), then reduces its
