@@ -272,6 +272,19 @@ bool Heap::contains(const void* p, size_t bytes, size_t& off) const {
   return true;
 }
 
+void Heap::reset_allocator(size_t total, size_t reserved_bytes, void* fake_base) {
+  std::lock_guard<std::mutex> g(mu_);
+  size = total;
+  reserved = reserved_bytes;
+  rank = 0;
+  n = 1;
+  base.assign(1, (CUdeviceptr)(uintptr_t)fake_base);
+  peer_handle.assign(1, 0);
+  free_.clear();
+  live_.clear();
+  free_[reserved] = size - reserved;
+}
+
 size_t Heap::used() const {
   std::lock_guard<std::mutex> g(mu_);
   size_t u = 0;

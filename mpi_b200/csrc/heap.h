@@ -61,6 +61,8 @@ struct Heap {
   int free_off(size_t off);
   bool contains(const void* p, size_t bytes, size_t& off) const;
   size_t used() const;
+  // Allocator-only initialisation (no device memory): host unit tests of alloc/free_off/contains.
+  void reset_allocator(size_t total, size_t reserved_bytes, void* fake_base);
 
   size_t reserved = 0; // control region
  private:

@@ -76,3 +76,13 @@ def test_cpp_facade_host_logic():
                            "-L" + lib, "-lb200mpi", "-Wl,-rpath," + lib, "-pthread"])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
     assert out.returncode == 0 and "facade ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_heap_allocator_unit():
+    """First-fit sub-allocator of the device heap: granules, reuse, coalescing, exhaustion, stress."""
+    import tempfile
+    exe = os.path.join(tempfile.mkdtemp(prefix="b200mpi-heap-"), "heap_alloc_test")
+    subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "tests", "cpp", "heap_alloc_test.cpp"),
+                           os.path.join(ROOT, "mpi_b200", "csrc", "heap.cpp"), os.path.join(ROOT, "mpi_b200", "csrc", "ctrl.cpp"), "-cudart", "static", "-lpthread"])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "heap allocator ok" in out.stdout, out.stdout + out.stderr
