@@ -34,8 +34,7 @@ type Cuda struct {
 	Addrs    []string      // addresses of all processes (-mpi-alladdr)
 	Timeout  time.Duration // Init fails after this long (-mpi-inittimeout); 0 waits forever
 	Password string        // compared during the handshake (-mpi-password)
-	Gpu      int           // CUDA ordinal; <0 means rank % device count (-mpi-gpu)
-	gpuSet   bool
+	Gpu      *int          // CUDA ordinal; nil takes -mpi-gpu (default -1: rank % device count)
 }
 
 const (
@@ -102,9 +101,9 @@ func (c *Cuda) Init() error {
 	if len(c.Addrs) == 0 {
 		c.Addrs = append([]string(nil), FlagAllAddrs...)
 	}
-	gpu := c.Gpu
-	if !c.gpuSet && c.Gpu == 0 {
-		gpu = FlagGpu
+	gpu := FlagGpu
+	if c.Gpu != nil {
+		gpu = *c.Gpu
 	}
 	addr, all, pw := C.CString(c.Addr), C.CString(strings.Join(c.Addrs, ",")), C.CString(c.Password)
 	defer C.free(unsafe.Pointer(addr))
