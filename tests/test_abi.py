@@ -33,6 +33,19 @@ def test_library_exports_every_declared_symbol():
     assert exported == names, "library exports symbols the header does not declare (or vice versa)"
 
 
+def test_header_is_plain_c():
+    """The boundary is a C ABI: the header must compile as C99 with nothing but libc headers."""
+    import tempfile
+    src = os.path.join(tempfile.mkdtemp(prefix="b200mpi-hdr-"), "t.c")
+    with open(src, "w") as f:
+        f.write('#include "b200mpi.h"\nint main(void) { return b200mpi_rank() == -1 && B200MPI_MAX_RANKS == 8 ? 0 : 1; }\n')
+    exe = src[:-2]
+    lib = os.path.join(ROOT, "mpi_b200", "lib")
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+                           "-L" + lib, "-lb200mpi", "-Wl,-rpath," + lib])
+    assert subprocess.run([exe]).returncode == 0  # links against the real library and answers like the reference before Init
+
+
 def test_no_link_time_dependency_on_libcuda_or_torch():
     out = subprocess.run(["ldd", mpi.LIB_PATH], capture_output=True, text=True).stdout
     assert "libcuda.so" not in out and "torch" not in out and "nccl" not in out
