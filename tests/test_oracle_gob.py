@@ -133,3 +133,46 @@ def test_restated_tcp_path_delivers_exact_values(n):
     assert np.array_equal(out, O.fill(np.float32, 0xB2000000, 1000))
     secs, out = O.ref_bench(O.COLL_ALLREDUCE_NAIVE, np.float64, n, 1000, iters=1, warmup=1)
     assert np.array_equal(out, O.allreduce([O.fill(np.float64, 0xB2000000 + r, 1000) for r in range(n)], order=O.ORDER_RANK))
+
+
+# ---- an independent restatement of the same published rules, in Python, to cross-check oracle/gob.c
+def _py_uint(u):
+    if u < 128:
+        return bytes([u])
+    b = u.to_bytes((u.bit_length() + 7) // 8, "big")
+    return bytes([256 - len(b)]) + b
+
+
+def _py_int(i):
+    return _py_uint(((~i) << 1 | 1) & (2**64 - 1) if i < 0 else i << 1)
+
+
+def _py_float(f):
+    import struct
+    return _py_uint(int.from_bytes(struct.pack("<d", float(f)), "big"))  # float64 bits, byte-reversed
+
+
+def _py_slice_stream(arr):
+    name, elem, enc = {
+        np.dtype(np.float64): (b"[]float64", 4, _py_float), np.dtype(np.float32): (b"[]float32", 4, _py_float),
+        np.dtype(np.int64): (b"[]int64", 2, lambda v: _py_int(int(v)))}[arr.dtype]
+    td = _py_int(-65) + b"\x02\x01\x01" + _py_uint(len(name)) + name + b"\x01" + _py_int(65) + b"\x00\x01" + _py_int(elem) + b"\x00\x00"
+    body = _py_int(65) + b"\x00" + _py_uint(arr.size) + b"".join(enc(v) for v in arr)
+    return _py_uint(len(td)) + td + _py_uint(len(body)) + body
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.int64])
+def test_c_encoder_matches_independent_python_encoder(dtype):
+    rng = np.random.default_rng(3)
+    for count in (0, 1, 7, 200):
+        if dtype == np.int64:
+            x = rng.integers(-2**63, 2**63 - 1, count, dtype=np.int64)
+            if count >= 7:
+                x[:7] = [0, 1, -1, 63, 64, -64, -65]
+        else:
+            x = (rng.standard_normal(count) * 10.0 ** rng.integers(-30, 30, count)).astype(dtype)
+            if count >= 7:
+                x[:7] = [0.0, -0.0, 1.0, 17.0, 0.5, np.inf, -np.inf]
+        assert O.gob_encode(x) == _py_slice_stream(x), (dtype, count)
+    raw = bytes(range(256)) * 3
+    assert O.gob_encode(raw) == _py_uint(len(_py_int(5) + b"\x00" + _py_uint(len(raw)) + raw)) + _py_int(5) + b"\x00" + _py_uint(len(raw)) + raw
