@@ -143,6 +143,39 @@ def main():
         send.free()
         recv.free()
 
+    if "latency" in colls and n > 1:
+        # blocking-call latency of small Allreduce (what a Go caller sees per call): device-resident and
+        # pinned-host buffers, every algorithm incl. the experimental LL path; median of 200 calls
+        hin, hout = ctypes.c_void_p(), ctypes.c_void_p()
+        lib.b200mpi_host_alloc(1 << 16, ctypes.byref(hin))
+        lib.b200mpi_host_alloc(1 << 16, ctypes.byref(hout))
+        ctypes.memset(hin.value, 0, 1 << 16)
+        dsend = mpi.Alloc(1 << 14, np.float32).copy_from_host(np.full(1 << 14, rank + 1, dtype=np.float32))
+        drecv = mpi.Alloc(1 << 14, np.float32)
+        for algo in ("auto", "oneshot", "twoshot", "nvls", "ll"):
+            if algo == "nvls" and not nvls:
+                continue
+            lib.b200mpi_set_algo(L.COLL_ALLREDUCE, ALGOS[algo])
+            for S in (8, 64, 512, 4096, 32768):
+                cnt = S // 4
+                for kind, sp, rp, mk in (("device", dsend.ptr, drecv.ptr, L.DEVICE), ("host", hin, hout, L.HOST)):
+                    ts = []
+                    for i in range(220):
+                        mpi.Barrier() if i % 50 == 0 else None
+                        t0 = time.perf_counter()
+                        rc = lib.b200mpi_allreduce(sp, rp, cnt, L.F32, L.SUM, mk)
+                        ts.append(time.perf_counter() - t0)
+                        if rc:
+                            raise RuntimeError(L.last_error())
+                    ts = sorted(ts[20:])
+                    emit({"coll": "latency", "dtype": "f32", "algo": algo, "kind": kind, "bytes": S, "t_call_us_median": maxr(ts[len(ts) // 2]) * 1e6,
+                          "t_call_us_p10": maxr(ts[len(ts) // 10]) * 1e6, "t_us": maxr(ts[len(ts) // 2]) * 1e6, "busbw_gbs": 0.0, "ok": True})
+        lib.b200mpi_set_algo(L.COLL_ALLREDUCE, 0)
+        lib.b200mpi_host_free(hin)
+        lib.b200mpi_host_free(hout)
+        dsend.free()
+        drecv.free()
+
     if "bcast" in colls and n > 1:
         buf = mpi.Alloc(maxc, np.float32)
         for algo in ("oneshot", "twoshot", "nvls"):
