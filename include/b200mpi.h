@@ -50,7 +50,8 @@ typedef enum {
 typedef enum {
   B200MPI_COLL_ALLREDUCE = 0,
   B200MPI_COLL_BCAST = 1,
-  B200MPI_COLL_ALLGATHER = 2
+  B200MPI_COLL_ALLGATHER = 2,
+  B200MPI_COLL_REDUCE_SCATTER = 3
 } b200mpi_coll;
 
 typedef enum {
@@ -62,7 +63,8 @@ typedef enum {
   B200MPI_ALGO_RING = 3,    /* allreduce/allgather: 2(n-1) / (n-1) neighbour steps */
   B200MPI_ALGO_NVLS = 4,    /* multimem.ld_reduce / multimem.st through the NVSwitch */
   B200MPI_ALGO_TWOSHOT_SMEM = 5, /* allreduce two-shot with cp.async.bulk shared-memory staging */
-  B200MPI_ALGO_LL = 6        /* allreduce <= 32 KiB: flag-in-data cells, no barrier (experimental) */
+  B200MPI_ALGO_LL = 6,       /* allreduce <= 256 KiB: flag-in-data cells, no barrier (the small-message default) */
+  B200MPI_ALGO_HYBRID = 7    /* allreduce: NVLS for most of the message + fused P2P two-shot for the rest, one kernel */
 } b200mpi_algo;
 
 typedef enum {
@@ -104,18 +106,26 @@ const char* b200mpi_last_error(void); /* thread-local, never NULL */
  * Buffers from here take the zero-copy path; any other device pointer is staged through it. */
 int b200mpi_alloc(size_t bytes, void** dptr);
 int b200mpi_free(void* dptr);
-/* Pinned host memory (optional; plain malloc'ed memory works too, slower). */
+/* Pinned host memory on the NUMA node of this rank's GPU (optional; plain malloc'ed / Go memory
+ * works too: it is staged through a pinned bounce ring by helper threads). */
 int b200mpi_host_alloc(size_t bytes, void** hptr);
 int b200mpi_host_free(void* hptr);
 /* Synchronous copies for harnesses that have no CUDA binding of their own. kind: 0 H2D, 1 D2H, 2 D2D */
 int b200mpi_memcpy(void* dst, const void* src, size_t bytes, int kind);
 int b200mpi_heap_info(size_t* total, size_t* used, int* nvls_available);
+int b200mpi_numa_node(void); /* NUMA node of the bound GPU (sysfs), -1 unknown */
 
 /* ---- point to point: mpi.Send / mpi.Receive (mpi.go:126,157; network.go:518-602) ----------- */
 
 /* Synchronous (rendezvous) send: returns once the matching recv has taken the data, like the
  * reference's ack wait (network.go:569).  dest == own rank is legal (network.go:545-548). */
 int b200mpi_send(const void* buf, size_t count, int dtype, int dest, int tag, int memkind);
+/* The Send/Wait pair sketched in the reference (mpi.go:132-152, commented out there): isend
+ * returns once the data has left the caller's buffer ("sent on connection", here: staged in this
+ * rank's device heap), without waiting for the receiver; wait blocks until `dest` confirmed the
+ * message with `tag` and frees the {dest, tag} pair.  Every isend must be followed by one wait. */
+int b200mpi_isend(const void* buf, size_t count, int dtype, int dest, int tag, int memkind);
+int b200mpi_wait(int dest, int tag);
 /* Blocks for message (src, tag).  *count_out = elements sent (gob resizes the destination,
  * network.go:597); more than `capacity` elements => B200MPI_ERR_TRUNCATE, *count_out = needed. */
 int b200mpi_recv(void* buf, size_t capacity, size_t* count_out, int dtype, int src, int tag,
@@ -128,12 +138,21 @@ int b200mpi_bcast(void* buf, size_t count, int dtype, int root, int memkind);
 int b200mpi_allreduce(const void* send, void* recv, size_t count, int dtype, int op, int memkind);
 /* recv holds size()*count_per_rank elements, rank r's block at r*count_per_rank. */
 int b200mpi_allgather(const void* send, void* recv, size_t count_per_rank, int dtype, int memkind);
+/* send holds size()*count_per_rank elements; rank j receives op over r of rank r's block j
+ * (rank order).  recv may be the caller's own block of send (in place).  This is the first half
+ * of the two-shot Allreduce on its own. */
+int b200mpi_reduce_scatter(const void* send, void* recv, size_t count_per_rank, int dtype, int op, int memkind);
+/* Allreduce whose result lands on `root` only (recv may be NULL elsewhere). */
+int b200mpi_reduce(const void* send, void* recv, size_t count, int dtype, int op, int root, int memkind);
+/* send and recv hold size()*count_per_rank elements; block j of send becomes block rank() of rank j's recv. */
+int b200mpi_alltoall(const void* send, void* recv, size_t count_per_rank, int dtype, int memkind);
 int b200mpi_barrier(void);
 
 /* Enqueue-only forms on the library stream (DEVICE memkind only). */
 int b200mpi_bcast_async(void* buf, size_t count, int dtype, int root);
 int b200mpi_allreduce_async(const void* send, void* recv, size_t count, int dtype, int op);
 int b200mpi_allgather_async(const void* send, void* recv, size_t count_per_rank, int dtype);
+int b200mpi_reduce_scatter_async(const void* send, void* recv, size_t count_per_rank, int dtype, int op);
 int b200mpi_stream_sync(void); /* waits and reports device-side watchdog errors */
 
 /* ---- tuning / measurement ------------------------------------------------------------------ */
@@ -142,7 +161,10 @@ int b200mpi_set_algo(int coll, int algo); /* force an algorithm (benches, tests)
 int b200mpi_get_algo(int coll, size_t count, int dtype); /* what AUTO resolves to (>=1) or <0 */
 int b200mpi_set_max_blocks(int blocks); /* cap grid size (0 = default: SMs x occupancy) */
 /* Tuning knobs for sweeps: "twoshot_unroll" (0|1), "nvls_unroll" (1|2|4|8), "nvls_min_ranks",
- * "oneshot_max_bytes", "stage_chunk". */
+ * "nvls_max_blocks", "oneshot_max_bytes", "ll_max_bytes", "stage_chunk", "pipe_min_bytes",
+ * "pipe_chunk_bytes", "bounce_chunk_bytes", "host_threads", "own_block_bytes", "copy_variant",
+ * "hybrid_p2p_permille", "hybrid_p2p_blocks", "hybrid_min_bytes", "bcast_nvls2", "bcast_nvls_min",
+ * "allgather_nvls_min". */
 int b200mpi_set_param(const char* name, int64_t value);
 /* cudaStream_t used for collectives; set NULL to restore the library's own stream. */
 int b200mpi_get_stream(void** stream);

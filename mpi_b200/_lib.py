@@ -13,9 +13,9 @@ LIB_PATH = os.path.join(_HERE, "lib", "libb200mpi.so")
 U8, I64, F32, F64 = 0, 1, 2, 3
 SUM, MAX, MIN = 0, 1, 2
 HOST, DEVICE = 0, 1
-COLL_ALLREDUCE, COLL_BCAST, COLL_ALLGATHER = 0, 1, 2
-ALGO_AUTO, ALGO_ONESHOT, ALGO_TWOSHOT, ALGO_RING, ALGO_NVLS, ALGO_TWOSHOT_SMEM, ALGO_LL = 0, 1, 2, 3, 4, 5, 6
-ALGO_NAMES = {0: "auto", 1: "oneshot", 2: "twoshot", 3: "ring", 4: "nvls", 5: "twoshot_smem", 6: "ll"}
+COLL_ALLREDUCE, COLL_BCAST, COLL_ALLGATHER, COLL_REDUCE_SCATTER = 0, 1, 2, 3
+ALGO_AUTO, ALGO_ONESHOT, ALGO_TWOSHOT, ALGO_RING, ALGO_NVLS, ALGO_TWOSHOT_SMEM, ALGO_LL, ALGO_HYBRID = 0, 1, 2, 3, 4, 5, 6, 7
+ALGO_NAMES = {0: "auto", 1: "oneshot", 2: "twoshot", 3: "ring", 4: "nvls", 5: "twoshot_smem", 6: "ll", 7: "hybrid"}
 
 OK = 0
 ERR_ARG, ERR_NOT_INIT, ERR_BOOTSTRAP, ERR_PASSWORD, ERR_TIMEOUT, ERR_TAG_EXISTS = -1, -2, -3, -4, -5, -6
@@ -38,10 +38,17 @@ SYMBOLS = {
     "b200mpi_memcpy": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_int]),
     "b200mpi_heap_info": (_c.c_int, [_c.POINTER(_c.c_size_t), _c.POINTER(_c.c_size_t), _c.POINTER(_c.c_int)]),
     "b200mpi_send": (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.c_int, _c.c_int, _c.c_int, _c.c_int]),
+    "b200mpi_isend": (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.c_int, _c.c_int, _c.c_int, _c.c_int]),
+    "b200mpi_wait": (_c.c_int, [_c.c_int, _c.c_int]),
     "b200mpi_recv": (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.POINTER(_c.c_size_t), _c.c_int, _c.c_int, _c.c_int, _c.c_int]),
     "b200mpi_bcast": (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.c_int, _c.c_int, _c.c_int]),
     "b200mpi_allreduce": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_int, _c.c_int, _c.c_int]),
     "b200mpi_allgather": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_int, _c.c_int]),
+    "b200mpi_reduce_scatter": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_int, _c.c_int, _c.c_int]),
+    "b200mpi_reduce": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_int, _c.c_int, _c.c_int, _c.c_int]),
+    "b200mpi_alltoall": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_int, _c.c_int]),
+    "b200mpi_reduce_scatter_async": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_int, _c.c_int]),
+    "b200mpi_numa_node": (_c.c_int, []),
     "b200mpi_barrier": (_c.c_int, []),
     "b200mpi_bcast_async": (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.c_int, _c.c_int]),
     "b200mpi_allreduce_async": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_int, _c.c_int]),

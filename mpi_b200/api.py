@@ -5,6 +5,9 @@ Same names, same argument meaning, same blocking behaviour:
     Init() Finalize() Rank() Size() Send(data, destination, tag) Receive(data, source, tag)
     Register(impl)  Interface  Raw  TagExists                       (the reference's surface)
     Recv  Bcast(data, root)  Allreduce(send, recv, op)  Allgather(send, recv)  Barrier()   (new)
+    ReduceScatter(send, recv, op)  Reduce(send, recv, op, root)  Alltoall(send, recv)      (new)
+    Isend(data, destination, tag) + Wait(destination, tag)     (the Send/Wait design commented out
+                                                                in the reference, mpi.go:132-152)
 
 Where Go returns `error`, Python raises MpiError (Go's "implementations may panic", mpi.go:20-21,
 maps to the same exception).  `data` is type-switched exactly like the cgo shim
@@ -196,6 +199,16 @@ class Cuda(Interface):
         ptr, count, dt, kind, keep, _ = _describe(data)
         _check(L.load().b200mpi_send(ptr, count, dt, int(destination), int(tag), kind), tag)
 
+    def Isend(self, data, destination, tag):
+        """mpi.go:132-143 (commented design): returns once `data` may be modified again, without
+        waiting for the receiver; Wait(destination, tag) collects the confirmation."""
+        ptr, count, dt, kind, keep, _ = _describe(data)
+        _check(L.load().b200mpi_isend(ptr, count, dt, int(destination), int(tag), kind), tag)
+
+    def Wait(self, destination, tag):
+        """mpi.go:146-152 (commented design)."""
+        _check(L.load().b200mpi_wait(int(destination), int(tag)), tag)
+
     def Receive(self, data, source, tag):
         """Fills `data` and returns the received value.  numpy arrays and bytearrays are filled
         in place when large enough (a view of the received length is returned), otherwise a new
@@ -259,6 +272,34 @@ class Cuda(Interface):
         if rc_ != sc * self.Size() or sdt != rdt or sk != rk:
             raise ValueError("mpi: Allgather recv must hold Size()*len(send) elements of the same type and memory kind")
         _check(L.load().b200mpi_allgather(sp, rp, sc, sdt, sk))
+        return recv
+
+    def ReduceScatter(self, send, recv, op=SUM):
+        sp, sc, sdt, sk, _, _ = _describe(send)
+        rp, rc_, rdt, rk, _, _ = _describe(recv)
+        if sc != rc_ * self.Size() or sdt != rdt or sk != rk:
+            raise ValueError("mpi: ReduceScatter send must hold Size()*len(recv) elements of the same type and memory kind")
+        _check(L.load().b200mpi_reduce_scatter(sp, rp, rc_, sdt, int(op), sk))
+        return recv
+
+    def Reduce(self, send, recv, op=SUM, root=0):
+        sp, sc, sdt, sk, _, _ = _describe(send)
+        if recv is None:
+            rp = None
+        else:
+            rp, rc_, rdt, rk, _, _ = _describe(recv)
+            if sc != rc_ or sdt != rdt or sk != rk:
+                raise ValueError("mpi: Reduce send and recv must have the same length, type and memory kind")
+        _check(L.load().b200mpi_reduce(sp, rp, sc, sdt, int(op), int(root), sk))
+        return recv
+
+    def Alltoall(self, send, recv):
+        sp, sc, sdt, sk, _, _ = _describe(send)
+        rp, rc_, rdt, rk, _, _ = _describe(recv)
+        n = self.Size()
+        if sc != rc_ or sc % max(n, 1) or sdt != rdt or sk != rk:
+            raise ValueError("mpi: Alltoall send and recv must both hold Size() equal blocks of the same type and memory kind")
+        _check(L.load().b200mpi_alltoall(sp, rp, sc // n, sdt, sk))
         return recv
 
     def Barrier(self):
@@ -333,3 +374,23 @@ def Allgather(send, recv):
 
 def Barrier():
     return _collective("Barrier")()
+
+
+def ReduceScatter(send, recv, op=SUM):
+    return _collective("ReduceScatter")(send, recv, op)
+
+
+def Reduce(send, recv, op=SUM, root=0):
+    return _collective("Reduce")(send, recv, op, root)
+
+
+def Alltoall(send, recv):
+    return _collective("Alltoall")(send, recv)
+
+
+def Isend(data, destination, tag):
+    return _collective("Isend")(data, destination, tag)
+
+
+def Wait(destination, tag):
+    return _collective("Wait")(destination, tag)

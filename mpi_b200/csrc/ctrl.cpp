@@ -412,11 +412,21 @@ int Ctrl::init(const char* addr_c, const char* csv_c, const char* pw_c, int64_t 
     return dial_rc;
   }
 
-  // Agree on a nonce (rank 0's) and open the per-pair unix sockets used for fd passing.
-  std::vector<uint64_t> nonces(n);
-  int rc = allgather(&nonce, sizeof nonce, nonces.data(), err);
+  // Agree on a nonce and a secret (rank 0's), both carried by the password-checked TCP mesh, and
+  // open the per-pair unix sockets used for fd passing.  The socket names are visible in
+  // /proc/net/unix, so a connection only counts after (a) SO_PEERCRED shows this user's uid and
+  // (b) the peer presented the secret -- before that no allocation handle is sent to it.
+  struct Agree { uint64_t nonce, secret[2]; } mine_a, all_a[B200MPI_MAX_RANKS];
+  {
+    std::random_device rd2;
+    mine_a.nonce = nonce;
+    mine_a.secret[0] = ((uint64_t)rd2() << 32) ^ rd2();
+    mine_a.secret[1] = ((uint64_t)rd2() << 32) ^ rd2();
+  }
+  int rc = allgather(&mine_a, sizeof mine_a, all_a, err);
   if (rc) return rc;
-  nonce = nonces[0];
+  nonce = all_a[0].nonce;
+  const uint64_t secret[2] = {all_a[0].secret[0], all_a[0].secret[1]};
   int ul = ::socket(AF_UNIX, SOCK_STREAM, 0);
   sockaddr_un usa;
   socklen_t ulen = fill_abstract(usa, uds_name(nonce, rank));
@@ -430,6 +440,7 @@ int Ctrl::init(const char* addr_c, const char* csv_c, const char* pw_c, int64_t 
     ::close(ul);
     return rc;
   }
+  struct UdsHello { int32_t who; int32_t pad; uint64_t secret[2]; };
   for (int peer = 0; peer < rank; ++peer) { // higher rank connects to lower rank
     int c = ::socket(AF_UNIX, SOCK_STREAM, 0);
     sockaddr_un psa;
@@ -440,21 +451,32 @@ int Ctrl::init(const char* addr_c, const char* csv_c, const char* pw_c, int64_t 
       ::close(ul);
       return B200MPI_ERR_BOOTSTRAP;
     }
-    int32_t me = rank;
-    write_full(c, &me, sizeof me);
+    UdsHello h = {rank, 0, {secret[0], secret[1]}};
+    write_full(c, &h, sizeof h);
     uds_fd[peer] = c;
   }
-  for (int k = rank + 1; k < n; ++k) {
-    int c = ::accept(ul, nullptr, nullptr);
-    int32_t who = -1;
-    Deadline d2(timeout_ns);
-    if (c < 0 || read_full(c, &who, sizeof who, d2) || who <= rank || who >= n || uds_fd[who] != -1) {
-      err = "unix socket accept failed";
-      if (c >= 0) ::close(c);
+  Deadline d2(timeout_ns > 0 ? timeout_ns : 60000000000ll);
+  for (int got = rank + 1; got < n;) {
+    struct pollfd pf = {ul, POLLIN, 0};
+    int pr;
+    do { pr = ::poll(&pf, 1, d2.poll_ms()); } while (pr < 0 && errno == EINTR);
+    int c = pr > 0 ? ::accept(ul, nullptr, nullptr) : -1;
+    if (c < 0) {
+      err = "unix socket accept failed or timed out";
       ::close(ul);
       return B200MPI_ERR_BOOTSTRAP;
     }
-    uds_fd[who] = c;
+    struct ucred cred = {};
+    socklen_t clen = sizeof cred;
+    UdsHello h = {};
+    const bool cred_ok = getsockopt(c, SOL_SOCKET, SO_PEERCRED, &cred, &clen) == 0 && cred.uid == geteuid();
+    if (!cred_ok || read_full(c, &h, sizeof h, d2) || h.secret[0] != secret[0] || h.secret[1] != secret[1] ||
+        h.who <= rank || h.who >= n || uds_fd[h.who] != -1) {
+      ::close(c); // a stranger (or a duplicate): not a rank of this world, keep waiting for the real one
+      continue;
+    }
+    uds_fd[h.who] = c;
+    ++got;
   }
   ::close(ul);
   return 0;

@@ -124,7 +124,7 @@ int Heap::create(Driver& drv, Ctrl& ctrl, int device, size_t bytes, bool want_nv
       return B200MPI_ERR_CUDA;
     }
   }
-  reserved = 2u << 20;
+  reserved = kHeapReserved;
   if (cudaMemset((void*)base[rank], 0, reserved) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
     err = std::string("heap control region clear failed: ") + cudaGetErrorString(cudaGetLastError());
     return B200MPI_ERR_CUDA;

@@ -17,6 +17,9 @@
 
 namespace b200 {
 
+// Control region at the start of every heap: barrier slots, ring flags, LL cells (kernels.cuh: kCtrlBytes).
+constexpr size_t kHeapReserved = 16u << 20;
+
 // Driver entry points resolved through cudaGetDriverEntryPoint (no link-time libcuda dependency,
 // so the library still loads on a box without a driver and fails loudly at init instead).
 struct Driver {

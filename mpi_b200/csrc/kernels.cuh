@@ -27,11 +27,18 @@ namespace b200 {
 
 constexpr int kMaxRanks = 8;
 constexpr int kMaxBlocks = 592;            // 148 SMs x 4
-constexpr size_t kCtrlBytes = 2u << 20;    // control region at the start of every heap
+constexpr size_t kCtrlBytes = 16u << 20;   // control region at the start of every heap (== kHeapReserved, heap.h)
 constexpr size_t kRingFlagsOff = 512u << 10;
-constexpr size_t kLLOff = 1u << 20;          // LL cells: [parity 2][src rank 8][kLLCells] x 16 B = 1 MiB
-constexpr size_t kLLCells = 4096;            // 8 payload bytes per cell -> 32 KiB per call
+constexpr size_t kLLStateOff = 768u << 10;   // LL bookkeeping words (device-resident sequence number, CTA counter)
+constexpr size_t kLLOff = 1u << 20;          // LL cells: [parity 2][src rank 8][kLLCells] x 16 B = 8 MiB
+constexpr size_t kLLCells = 32768;           // 8 payload bytes per cell -> 256 KiB per call
 constexpr int kThreads = 512;
+// Every collective launch consumes exactly kEpochStride flag values, whatever the algorithm:
+// start barrier = epoch, mid barriers = epoch+1 .. epoch+kEpochStride-2, end barrier =
+// epoch+kEpochStride-1.  Ranks that disagreed about a call (B200MPI_ERR_PEER) therefore still
+// agree about the epoch of the next one.
+constexpr uint32_t kEpochStride = 4096;
+constexpr uint32_t kMaxMids = kEpochStride - 2;
 
 struct __align__(32) Slot {
   uint32_t flag;
@@ -42,6 +49,8 @@ struct __align__(32) Slot {
 };
 static_assert(sizeof(Slot) == 32, "slot size");
 static_assert(sizeof(Slot) * kMaxBlocks * kMaxRanks <= kRingFlagsOff, "control region layout");
+static_assert(kRingFlagsOff + 4 * kMaxBlocks <= kLLStateOff && kLLStateOff + 4096 <= kLLOff, "control region layout");
+static_assert(kLLOff + 2 * kMaxRanks * kLLCells * 16 <= kCtrlBytes, "control region layout");
 
 struct Comm {
   char* base[kMaxRanks];     // heap of rank r as mapped in this process
@@ -81,7 +90,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 
 // Spin until *p >= want (wrap-safe).  On watchdog expiry raises the host-visible status word
 // and gives up so the kernel can drain; the host then reports B200MPI_ERR_TIMEOUT.
-__device__ __forceinline__ void wait_flag(const uint32_t* p, uint32_t want, const Comm& c) {
+__device__ __forceinline__ bool wait_flag(const uint32_t* p, uint32_t want, const Comm& c) {
   unsigned long long t0 = 0;
   uint32_t it = 0;
   while ((int32_t)(ld_acquire_sys(p) - want) < 0) {
@@ -91,10 +100,11 @@ __device__ __forceinline__ void wait_flag(const uint32_t* p, uint32_t want, cons
       else if (c.timeout_ns && now - t0 > c.timeout_ns) {
         *(volatile uint32_t*)c.status = 1u;
         __threadfence_system();
-        return;
+        return false;
       }
     }
   }
+  return true;
 }
 
 __device__ __forceinline__ Slot* slot_of(const Comm& c, int owner, int block, int src) {
@@ -102,9 +112,16 @@ __device__ __forceinline__ Slot* slot_of(const Comm& c, int owner, int block, in
 }
 
 // Per-CTA barrier #1: announce {a,b,sig} to every rank, wait for everyone's, publish the offsets
-// in smem.  Returns false (and raises status 2) when a peer's signature differs from ours -- ranks
-// called different collectives / counts / types -- so the body is skipped instead of touching
-// memory out of bounds; sync_end still runs, nobody hangs, the host reports B200MPI_ERR_PEER.
+// in smem.  Returns false when the body must not run:
+//   * a peer's signature differs from ours (status 2 -> B200MPI_ERR_PEER): ranks called different
+//     collectives / counts / types / grids, or
+//   * a peer did not show up within the watchdog time (status 1 -> B200MPI_ERR_TIMEOUT).
+// sync_end still runs, so nobody hangs, and no buffer is touched.
+// The signature covers the grid size.  CTAs other than 0 first look at what every peer's CTA 0
+// announced (slot row 0 of this rank's heap): if the peers launched a different grid, a CTA
+// without a partner learns it there instead of waiting for a flag that never comes.  (While the
+// grids match the row cannot be overwritten early: a peer's next kernel starts only after its
+// current one has finished, which needs this CTA to have passed sync_end.)
 __device__ __forceinline__ bool sync_start(const Comm& c, uint64_t a, uint64_t b, uint64_t* s_a,
                                            uint64_t* s_b) {
   __shared__ int s_bad;
@@ -117,15 +134,25 @@ __device__ __forceinline__ bool sync_start(const Comm& c, uint64_t a, uint64_t b
     st_relaxed_sys_u64(&theirs->b, b);
     st_relaxed_sys_u64(&theirs->c, c.sig);
     st_release_sys(&theirs->flag, c.epoch);
-    Slot* mine = slot_of(c, c.rank, blockIdx.x, t);
-    wait_flag(&mine->flag, c.epoch, c);
-    s_a[t] = ld_relaxed_sys_u64(&mine->a);
-    s_b[t] = ld_relaxed_sys_u64(&mine->b);
-    if (ld_relaxed_sys_u64(&mine->c) != c.sig) s_bad = 1;
+    bool ok = true;
+    if (blockIdx.x != 0) {
+      Slot* lead = slot_of(c, c.rank, 0, t);
+      if (!wait_flag(&lead->flag, c.epoch, c)) { s_bad = 2; ok = false; }
+      else if (ld_relaxed_sys_u64(&lead->c) != c.sig) { s_bad = 1; ok = false; }
+    }
+    if (ok) {
+      Slot* mine = slot_of(c, c.rank, blockIdx.x, t);
+      if (!wait_flag(&mine->flag, c.epoch, c)) s_bad = 2;
+      else {
+        s_a[t] = ld_relaxed_sys_u64(&mine->a);
+        s_b[t] = ld_relaxed_sys_u64(&mine->b);
+        if (ld_relaxed_sys_u64(&mine->c) != c.sig) s_bad = 1;
+      }
+    }
   }
   __syncthreads();
   if (s_bad) {
-    if (t == 0) {
+    if (t == 0 && s_bad == 1) {
       *(volatile uint32_t*)c.status = 2u;
       __threadfence_system();
     }
@@ -390,8 +417,12 @@ struct Owner {
 // traffic therefore overlap in both link directions and no mid barrier is needed.
 // In place is safe: a vector is read and then written only by its owner.
 // ---------------------------------------------------------------------------------------------
+// bid / nb: this CTA's index and the number of CTAs working on the message (a fused kernel may give
+// only part of its grid to this body).  only_dst >= 0: the reduced value is stored into that
+// rank's recv buffer only (Reduce); -1: into every rank's (Allreduce).
 template <typename T, typename Op, int NR, int UNROLL>
-__device__ __forceinline__ void twoshot_body(const Comm& c, const uint64_t* s_a, const uint64_t* s_b, size_t count, uint32_t shift) {
+__device__ __forceinline__ void twoshot_body(const Comm& c, const uint64_t* s_a, const uint64_t* s_b, size_t count, uint32_t shift,
+                                             unsigned bid, unsigned nb, int only_dst = -1) {
   const int n = NR ? NR : c.n;
   constexpr int R = NR ? NR : kMaxRanks;
   constexpr int EPV = Pack<T>::N;
@@ -399,18 +430,22 @@ __device__ __forceinline__ void twoshot_body(const Comm& c, const uint64_t* s_a,
   if (all_aligned16(s_a, s_b, n)) {
     const size_t nvec = count / EPV;
     const Owner own(nvec, shift, n, c.rank);
-    const char* src[R];
-    char* dst[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
+    // base pointers live in shared memory, not in 2 x R registers per thread (ptxas spilled the
+    // 8-rank and generic instances with register arrays)
+    __shared__ const char* src[kMaxRanks];
+    __shared__ char* dst[kMaxRanks];
+    if (tid < (size_t)R) {
+      const int r = (int)tid;
       const int q = r < n ? r : 0;
       src[r] = c.base[q] + s_a[q];
       // stores start at the next rank so the ranks do not all hit the same target at once
-      const int w = (c.rank + 1 + r) % n;
+      const int w = only_dst >= 0 ? only_dst : (c.rank + 1 + r) % n;
       dst[r] = c.base[w] + s_b[w];
     }
-    const size_t step = (size_t)gridDim.x * blockDim.x * UNROLL;
-    for (size_t l0 = (size_t)blockIdx.x * blockDim.x * UNROLL + tid; l0 < own.slots; l0 += step) {
+    __syncthreads();
+    const int ndst = only_dst >= 0 ? 1 : n;
+    const size_t step = (size_t)nb * blockDim.x * UNROLL;
+    for (size_t l0 = (size_t)bid * blockDim.x * UNROLL + tid; l0 < own.slots; l0 += step) {
       Pack<T> v[UNROLL][R];
       size_t gi[UNROLL];
 #pragma unroll
@@ -432,17 +467,18 @@ __device__ __forceinline__ void twoshot_body(const Comm& c, const uint64_t* s_a,
             if (r < n) acc = combine<T, Op>(acc, v[u][r]);
 #pragma unroll
           for (int r = 0; r < R; ++r)
-            if (r < n) st_pack<T>(dst[r] + gi[u] * 16, acc);
+            if (r < ndst) st_pack<T>(dst[r] + gi[u] * 16, acc);
         }
       }
     }
     // elements past the last whole vector: reduced and pushed by the last rank
     if (c.rank == n - 1) {
-      const size_t gtid = (size_t)blockIdx.x * blockDim.x + tid;
-      for (size_t e = nvec * EPV + gtid; e < count; e += (size_t)gridDim.x * blockDim.x) {
+      const size_t gtid = (size_t)bid * blockDim.x + tid;
+      for (size_t e = nvec * EPV + gtid; e < count; e += (size_t)nb * blockDim.x) {
         T acc = reinterpret_cast<const volatile T*>(c.base[0] + s_a[0])[e];
         for (int r = 1; r < n; ++r) acc = Op::template apply<T>(acc, reinterpret_cast<const volatile T*>(c.base[r] + s_a[r])[e]);
-        for (int r = 0; r < n; ++r) reinterpret_cast<volatile T*>(c.base[r] + s_b[r])[e] = acc;
+        for (int r = 0; r < n; ++r)
+          if (only_dst < 0 || r == only_dst) reinterpret_cast<volatile T*>(c.base[r] + s_b[r])[e] = acc;
       }
     }
   } else {
@@ -450,24 +486,25 @@ __device__ __forceinline__ void twoshot_body(const Comm& c, const uint64_t* s_a,
     const size_t per = (count + n - 1) / n;
     const size_t lo = per * c.rank < count ? per * c.rank : count;
     const size_t hi = lo + per < count ? lo + per : count;
-    for (size_t e = lo + (size_t)blockIdx.x * blockDim.x + tid; e < hi; e += (size_t)gridDim.x * blockDim.x) {
+    for (size_t e = lo + (size_t)bid * blockDim.x + tid; e < hi; e += (size_t)nb * blockDim.x) {
       T acc = reinterpret_cast<const volatile T*>(c.base[0] + s_a[0])[e];
       for (int r = 1; r < n; ++r) acc = Op::template apply<T>(acc, reinterpret_cast<const volatile T*>(c.base[r] + s_a[r])[e]);
-      for (int r = 0; r < n; ++r) reinterpret_cast<volatile T*>(c.base[r] + s_b[r])[e] = acc;
+      for (int r = 0; r < n; ++r)
+        if (only_dst < 0 || r == only_dst) reinterpret_cast<volatile T*>(c.base[r] + s_b[r])[e] = acc;
     }
   }
 }
 
 template <typename T, typename Op, int NR, int UNROLL>
 __global__ void __launch_bounds__(kThreads, 1)
-allreduce_twoshot_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t count, uint32_t shift) {
+allreduce_twoshot_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t count, uint32_t shift, int only_dst) {
   __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
   const bool call_ok = sync_start(c, send_off, recv_off, s_a, s_b);
   if (!call_ok) { // ranks disagree about this call: touch nothing, leave through the end barrier
     sync_end(c);
     return;
   }
-  twoshot_body<T, Op, NR, UNROLL>(c, s_a, s_b, count, shift);
+  twoshot_body<T, Op, NR, UNROLL>(c, s_a, s_b, count, shift, blockIdx.x, gridDim.x, only_dst);
   sync_end(c);
 }
 
@@ -754,54 +791,212 @@ __device__ __forceinline__ void multimem_st16(void* p, uint4 v) {
                : "memory");
 }
 
+// The switch part of a message: vectors [0, nvec) of the buffers at heap offsets send_off /
+// recv_off (the same on every rank).  only_dst < 0: the reduced vector is multicast into every
+// rank's recv buffer; >= 0: stored into that rank's recv buffer only (Reduce).
+template <typename T, typename Op, int UNROLL>
+__device__ __forceinline__ void nvls_body(const Comm& c, uint64_t send_off, uint64_t recv_off, size_t nvec, uint32_t shift,
+                                          unsigned bid, unsigned nb, int only_dst = -1) {
+  const Owner own(nvec, shift, c.n, c.rank);
+  const char* src = c.mc + send_off;
+  char* dst = only_dst < 0 ? c.mc + recv_off : c.base[only_dst] + recv_off;
+  const size_t tid = threadIdx.x;
+  const size_t step = (size_t)nb * blockDim.x * UNROLL;
+  for (size_t l0 = (size_t)bid * blockDim.x * UNROLL + tid; l0 < own.slots; l0 += step) {
+    Pack<T> v[UNROLL];
+    size_t gi[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const size_t l = l0 + (size_t)u * blockDim.x;
+      gi[u] = l < own.slots ? own.global(l) : nvec;
+      if (gi[u] < nvec) v[u] = Multimem<T, Op>::ld_reduce(src + gi[u] * 16);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      if (gi[u] < nvec) {
+        union { uint4 u4; Pack<T> k; } x;
+        x.k = v[u];
+        if (only_dst < 0) multimem_st16(dst + gi[u] * 16, x.u4);
+        else stg16(dst + gi[u] * 16, x.u4);
+      }
+    }
+  }
+}
+
+// count % EPV trailing elements of an aligned message: last rank, rank order, P2P.
+template <typename T, typename Op>
+__device__ __forceinline__ void tail_body(const Comm& c, const uint64_t* s_a, const uint64_t* s_b, size_t first, size_t count,
+                                          unsigned bid, unsigned nb, int only_dst = -1) {
+  const int n = c.n;
+  if (c.rank != n - 1) return;
+  for (size_t e = first + (size_t)bid * blockDim.x + threadIdx.x; e < count; e += (size_t)nb * blockDim.x) {
+    T acc = reinterpret_cast<const volatile T*>(c.base[0] + s_a[0])[e];
+    for (int r = 1; r < n; ++r) acc = Op::template apply<T>(acc, reinterpret_cast<const volatile T*>(c.base[r] + s_a[r])[e]);
+    for (int r = 0; r < n; ++r)
+      if (only_dst < 0 || r == only_dst) reinterpret_cast<volatile T*>(c.base[r] + s_b[r])[e] = acc;
+  }
+}
+
+__device__ __forceinline__ bool symmetric_offsets(const uint64_t* s_a, const uint64_t* s_b, uint64_t send_off, uint64_t recv_off, int n) {
+  bool sym = ((send_off | recv_off) & 15) == 0;
+  for (int r = 0; r < n; ++r) sym = sym && s_a[r] == send_off && s_b[r] == recv_off;
+  return sym;
+}
+
 template <typename T, typename Op, int UNROLL>
 __global__ void __launch_bounds__(kThreads, 1)
-allreduce_nvls_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t count, uint32_t shift) {
+allreduce_nvls_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t count, uint32_t shift, int only_dst) {
   __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
   const bool call_ok = sync_start(c, send_off, recv_off, s_a, s_b);
   if (!call_ok) { // ranks disagree about this call: touch nothing, leave through the end barrier
     sync_end(c);
     return;
   }
-  const int n = c.n;
   constexpr int EPV = Pack<T>::N;
-  bool symmetric = ((send_off | recv_off) & 15) == 0;
-  for (int r = 0; r < n; ++r) symmetric = symmetric && s_a[r] == send_off && s_b[r] == recv_off;
-  const size_t tid = threadIdx.x;
+  // Reduce (only_dst >= 0): recv matters on the root only; the other ranks' recv offsets are ignored
+  bool symmetric;
+  if (only_dst < 0) symmetric = symmetric_offsets(s_a, s_b, send_off, recv_off, c.n);
+  else {
+    symmetric = ((send_off | s_b[only_dst]) & 15) == 0;
+    for (int r = 0; r < c.n; ++r) symmetric = symmetric && s_a[r] == send_off;
+  }
   if (symmetric) {
     const size_t nvec = count / EPV;
-    const Owner own(nvec, shift, n, c.rank);
-    const char* src = c.mc + send_off;
-    char* dst = c.mc + recv_off;
-    const size_t step = (size_t)gridDim.x * blockDim.x * UNROLL;
-    for (size_t l0 = (size_t)blockIdx.x * blockDim.x * UNROLL + tid; l0 < own.slots; l0 += step) {
-      Pack<T> v[UNROLL];
-      size_t gi[UNROLL];
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const size_t l = l0 + (size_t)u * blockDim.x;
-        gi[u] = l < own.slots ? own.global(l) : nvec;
-        if (gi[u] < nvec) v[u] = Multimem<T, Op>::ld_reduce(src + gi[u] * 16);
-      }
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        if (gi[u] < nvec) {
-          union { uint4 u4; Pack<T> k; } x;
-          x.k = v[u];
-          multimem_st16(dst + gi[u] * 16, x.u4);
-        }
-      }
-    }
-    if (c.rank == n - 1) { // tail elements: last rank, rank order, P2P
-      for (size_t e = nvec * EPV + (size_t)blockIdx.x * blockDim.x + tid; e < count; e += (size_t)gridDim.x * blockDim.x) {
-        T acc = reinterpret_cast<const volatile T*>(c.base[0] + s_a[0])[e];
-        for (int r = 1; r < n; ++r) acc = Op::template apply<T>(acc, reinterpret_cast<const volatile T*>(c.base[r] + s_a[r])[e]);
-        for (int r = 0; r < n; ++r) reinterpret_cast<volatile T*>(c.base[r] + s_b[r])[e] = acc;
-      }
-    }
+    nvls_body<T, Op, UNROLL>(c, send_off, only_dst < 0 ? recv_off : s_b[only_dst], nvec, shift, blockIdx.x, gridDim.x, only_dst);
+    tail_body<T, Op>(c, s_a, s_b, nvec * EPV, count, blockIdx.x, gridDim.x, only_dst);
   } else {
     // the multicast address needs the same offsets on every rank; otherwise the P2P two-shot body
-    twoshot_body<T, Op, 0, 1>(c, s_a, s_b, count, shift);
+    twoshot_body<T, Op, 0, 1>(c, s_a, s_b, count, shift, blockIdx.x, gridDim.x, only_dst);
+  }
+  sync_end(c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Allreduce, hybrid: the switch reduction (multimem) saturates below the link rate
+// (profiles/r01: 256 MiB..1 GiB x 8 GPUs flat at ~480 GB/s algbw whatever the launch shape), so a
+// part of the message goes the P2P way at the same time: CTAs [0, nb_nvls) run nvls_body on
+// vectors [0, split), the remaining CTAs run the fused P2P two-shot body on [split, nvec) and the
+// tail.  Every element is still reduced exactly once by its owner and the same bits reach every
+// rank.  split and nb_nvls are functions of (count, n, tuning parameters) only.
+// ---------------------------------------------------------------------------------------------
+template <typename T, typename Op, int NR, int UN, int UP>
+__global__ void __launch_bounds__(kThreads, 1)
+allreduce_hybrid_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t count, uint32_t shift_nvls, uint32_t shift_p2p,
+                        size_t split_vec, unsigned nb_nvls) {
+  __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks], s_a2[kMaxRanks], s_b2[kMaxRanks];
+  const bool call_ok = sync_start(c, send_off, recv_off, s_a, s_b);
+  if (!call_ok) {
+    sync_end(c);
+    return;
+  }
+  constexpr int EPV = Pack<T>::N;
+  if (symmetric_offsets(s_a, s_b, send_off, recv_off, c.n)) {
+    if (blockIdx.x < nb_nvls) {
+      nvls_body<T, Op, UN>(c, send_off, recv_off, split_vec, shift_nvls, blockIdx.x, nb_nvls);
+    } else {
+      if (threadIdx.x < (unsigned)c.n) {
+        s_a2[threadIdx.x] = s_a[threadIdx.x] + split_vec * 16;
+        s_b2[threadIdx.x] = s_b[threadIdx.x] + split_vec * 16;
+      }
+      __syncthreads();
+      twoshot_body<T, Op, NR, UP>(c, s_a2, s_b2, count - split_vec * EPV, shift_p2p, blockIdx.x - nb_nvls, gridDim.x - nb_nvls);
+    }
+  } else {
+    twoshot_body<T, Op, NR, UP>(c, s_a, s_b, count, shift_p2p, blockIdx.x, gridDim.x);
+  }
+  sync_end(c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// ReduceScatter: rank j ends up with op over r of block j of rank r's send buffer (n blocks of
+// `count` elements), in rank order.  Only the owner reads block j, so recv may alias the owner's
+// own block of send.  P2P form: n concurrent read streams.  NVLS form: multimem.ld_reduce.
+// This is the first half of the two-shot allreduce exposed on its own.
+// ---------------------------------------------------------------------------------------------
+template <typename T, typename Op, int UNROLL>
+__global__ void __launch_bounds__(kThreads, 1)
+reduce_scatter_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t count) {
+  __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
+  __shared__ const char* src[kMaxRanks];
+  const bool call_ok = sync_start(c, send_off, recv_off, s_a, s_b);
+  if (!call_ok) {
+    sync_end(c);
+    return;
+  }
+  const int n = c.n;
+  constexpr int EPV = Pack<T>::N;
+  const size_t blk_bytes = count * sizeof(T);
+  if (threadIdx.x < (unsigned)n) src[threadIdx.x] = c.base[threadIdx.x] + s_a[threadIdx.x] + (size_t)c.rank * blk_bytes;
+  __syncthreads();
+  char* out = c.base[c.rank] + recv_off;
+  uint64_t m = recv_off | blk_bytes; // block j of every rank must be 16-byte aligned for the vector path
+  for (int r = 0; r < n; ++r) m |= s_a[r];
+  const size_t nvec = (m & 15) == 0 ? count / EPV : 0;
+  const size_t tid = threadIdx.x;
+  const size_t step = (size_t)gridDim.x * blockDim.x * UNROLL;
+  for (size_t i0 = (size_t)blockIdx.x * blockDim.x * UNROLL + tid; i0 < nvec; i0 += step) {
+    Pack<T> acc[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const size_t i = i0 + (size_t)u * blockDim.x;
+      if (i < nvec) {
+        acc[u] = ld_pack<T>(src[0] + i * 16);
+        for (int r = 1; r < n; ++r) acc[u] = combine<T, Op>(acc[u], ld_pack<T>(src[r] + i * 16));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const size_t i = i0 + (size_t)u * blockDim.x;
+      if (i < nvec) st_pack<T>(out + i * 16, acc[u]);
+    }
+  }
+  for (size_t e = nvec * EPV + (size_t)blockIdx.x * blockDim.x + tid; e < count; e += (size_t)gridDim.x * blockDim.x) {
+    T acc = reinterpret_cast<const volatile T*>(src[0])[e];
+    for (int r = 1; r < n; ++r) acc = Op::template apply<T>(acc, reinterpret_cast<const volatile T*>(src[r])[e]);
+    reinterpret_cast<T*>(out)[e] = acc;
+  }
+  sync_end(c);
+}
+
+template <typename T, typename Op, int UNROLL>
+__global__ void __launch_bounds__(kThreads, 1)
+reduce_scatter_nvls_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t count) {
+  __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
+  const bool call_ok = sync_start(c, send_off, recv_off, s_a, s_b);
+  if (!call_ok) {
+    sync_end(c);
+    return;
+  }
+  const int n = c.n;
+  constexpr int EPV = Pack<T>::N;
+  const size_t blk_bytes = count * sizeof(T);
+  bool symmetric = ((send_off | recv_off | blk_bytes) & 15) == 0;
+  for (int r = 0; r < n; ++r) symmetric = symmetric && s_a[r] == send_off && (s_b[r] & 15) == 0;
+  char* out = c.base[c.rank] + recv_off;
+  const size_t tid = threadIdx.x;
+  if (symmetric) {
+    const size_t nvec = count / EPV; // blk_bytes % 16 == 0: no tail
+    const char* src = c.mc + send_off + (size_t)c.rank * blk_bytes;
+    const size_t step = (size_t)gridDim.x * blockDim.x * UNROLL;
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x * UNROLL + tid; i0 < nvec; i0 += step) {
+      Pack<T> v[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const size_t i = i0 + (size_t)u * blockDim.x;
+        if (i < nvec) v[u] = Multimem<T, Op>::ld_reduce(src + i * 16);
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const size_t i = i0 + (size_t)u * blockDim.x;
+        if (i < nvec) st_pack<T>(out + i * 16, v[u]);
+      }
+    }
+  } else { // P2P, scalar, rank order (every rank takes this branch: the decision uses exchanged offsets only)
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + tid; e < count; e += (size_t)gridDim.x * blockDim.x) {
+      T acc = reinterpret_cast<const volatile T*>(c.base[0] + s_a[0] + (size_t)c.rank * blk_bytes)[e];
+      for (int r = 1; r < n; ++r) acc = Op::template apply<T>(acc, reinterpret_cast<const volatile T*>(c.base[r] + s_a[r] + (size_t)c.rank * blk_bytes)[e]);
+      reinterpret_cast<T*>(out)[e] = acc;
+    }
   }
   sync_end(c);
 }
@@ -1027,6 +1222,131 @@ bcast_nvls_kernel(Comm c, uint64_t buf_off, size_t bytes, int root) {
   sync_end(c);
 }
 
+// Bcast, scatter + multicast: the buffer is cut into ownership blocks (Owner, as in the allreduce);
+// the owner of a block fetches it from root with P2P loads (root owns blocks too and reads them
+// locally) and multicasts it into every rank's buffer with multimem.st.  Root's link carries every
+// byte once (read responses), every other rank's egress is S/n, and all ingress links fill at the
+// same time -- the root-only bcast_nvls_kernel is limited by one GPU's multimem.st rate instead.
+// Multicast stores also land in root's own buffer: identical bytes over identical bytes.
+template <int UNROLL>
+__global__ void __launch_bounds__(kThreads, 1)
+bcast_nvls2_kernel(Comm c, uint64_t buf_off, size_t bytes, int root, uint32_t shift) {
+  __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
+  const bool call_ok = sync_start(c, buf_off, buf_off, s_a, s_b);
+  if (!call_ok) {
+    sync_end(c);
+    return;
+  }
+  const int n = c.n;
+  bool symmetric = (buf_off & 15) == 0 && (bytes & 15) == 0;
+  for (int r = 0; r < n; ++r) symmetric = symmetric && s_a[r] == buf_off;
+  if (symmetric) {
+    const size_t nvec = bytes / 16;
+    const Owner own(nvec, shift, n, c.rank);
+    const char* src = c.base[root] + buf_off;
+    char* dst = c.mc + buf_off;
+    const size_t tid = threadIdx.x;
+    const size_t step = (size_t)gridDim.x * blockDim.x * UNROLL;
+    for (size_t l0 = (size_t)blockIdx.x * blockDim.x * UNROLL + tid; l0 < own.slots; l0 += step) {
+      uint4 v[UNROLL];
+      size_t gi[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const size_t l = l0 + (size_t)u * blockDim.x;
+        gi[u] = l < own.slots ? own.global(l) : nvec;
+        if (gi[u] < nvec) v[u] = ldg16(src + gi[u] * 16);
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+        if (gi[u] < nvec) multimem_st16(dst + gi[u] * 16, v[u]);
+    }
+  } else {
+    bcast_body<unsigned char, 1>(c, s_a, bytes, root, 1);
+  }
+  sync_end(c);
+}
+
+// Allgather through the switch: every rank streams its block once from local HBM into the
+// multicast address of its place in the recv buffer; per-GPU egress is one block instead of n-1.
+template <int UNROLL>
+__global__ void __launch_bounds__(kThreads, 1)
+allgather_nvls_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t bytes_per_rank) {
+  __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
+  const bool call_ok = sync_start(c, send_off, recv_off, s_a, s_b);
+  if (!call_ok) {
+    sync_end(c);
+    return;
+  }
+  const int n = c.n;
+  bool symmetric = ((recv_off | bytes_per_rank) & 15) == 0;
+  for (int r = 0; r < n; ++r) symmetric = symmetric && s_b[r] == recv_off && (s_a[r] & 15) == 0;
+  if (symmetric) {
+    const size_t nvec = bytes_per_rank / 16;
+    const char* src = c.base[c.rank] + send_off;
+    char* dst = c.mc + recv_off + (size_t)c.rank * bytes_per_rank;
+    const size_t step = (size_t)gridDim.x * blockDim.x * UNROLL;
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x * UNROLL + threadIdx.x; i0 < nvec; i0 += step) {
+      uint4 v[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const size_t i = i0 + (size_t)u * blockDim.x;
+        if (i < nvec) v[u] = ldg16(src + i * 16);
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const size_t i = i0 + (size_t)u * blockDim.x;
+        if (i < nvec) multimem_st16(dst + i * 16, v[u]);
+      }
+    }
+  } else {
+    allgather_push_body<unsigned char, 1>(c, s_a, s_b, bytes_per_rank);
+  }
+  sync_end(c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Alltoall: block j of rank r's send buffer becomes block r of rank j's recv buffer.  Direct
+// push, n write streams per GPU, targets rotated so that the ranks do not all hit one peer.
+// ---------------------------------------------------------------------------------------------
+template <typename U, int UNROLL>
+__device__ __forceinline__ void alltoall_body(const Comm& c, const uint64_t* s_a, const uint64_t* s_b, size_t bytes_per_block) {
+  const int n = c.n;
+  const size_t units = bytes_per_block / sizeof(U);
+  const size_t step = (size_t)gridDim.x * blockDim.x * UNROLL;
+  for (int k = 0; k < n; ++k) {
+    const int j = (c.rank + 1 + k) % n; // own block last
+    const U* src = reinterpret_cast<const U*>(c.base[c.rank] + s_a[c.rank] + (size_t)j * bytes_per_block);
+    U* dst = reinterpret_cast<U*>(c.base[j] + s_b[j] + (size_t)c.rank * bytes_per_block);
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x * UNROLL + threadIdx.x; i0 < units; i0 += step) {
+      U v[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const size_t i = i0 + (size_t)u * blockDim.x;
+        if (i < units) v[u] = src[i];
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const size_t i = i0 + (size_t)u * blockDim.x;
+        if (i < units) dst[i] = v[u];
+      }
+    }
+  }
+}
+
+template <typename U, int UNROLL>
+__global__ void __launch_bounds__(kThreads, 1)
+alltoall_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t bytes_per_block) {
+  __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
+  const bool call_ok = sync_start(c, send_off, recv_off, s_a, s_b);
+  if (!call_ok) {
+    sync_end(c);
+    return;
+  }
+  if (sizeof(U) == 1 || all_aligned_to(s_a, s_b, c.n, sizeof(U))) alltoall_body<U, UNROLL>(c, s_a, s_b, bytes_per_block);
+  else alltoall_body<unsigned char, 1>(c, s_a, s_b, bytes_per_block);
+  sync_end(c);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Point-to-point and local copies: dst <- src, `bytes` bytes, any alignment.  src may be a peer
 // mapping (receiver pulls the sender's posted region over NVLink).
@@ -1108,7 +1428,7 @@ template <> struct LLCodec<long long> {
 
 template <typename T, typename Op>
 __global__ void __launch_bounds__(256, 1)
-allreduce_ll_kernel(Comm c, const T* __restrict__ send, T* recv, size_t count, uint32_t seq) {
+allreduce_ll_kernel(Comm c, const T* __restrict__ send, T* recv, size_t count, uint32_t seq, uint32_t* done_host) {
   constexpr int EPC = LLCodec<T>::EPC;
   const size_t ncell = (count + EPC - 1) / EPC;
   const uint32_t parity = seq & 1u;
@@ -1155,6 +1475,21 @@ allreduce_ll_kernel(Comm c, const T* __restrict__ send, T* recv, size_t count, u
 #pragma unroll
     for (int k = 0; k < EPC; ++k)
       if (i * EPC + k < count) recv[i * EPC + k] = acc[k];
+  }
+  // Host-slice calls: send/recv are device-mapped pinned host buffers and the caller spins on
+  // *done_host instead of paying a stream synchronisation.  The last CTA to finish publishes seq
+  // after every CTA's result stores have been fenced at system scope.
+  if (done_host) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned* ctas = reinterpret_cast<unsigned*>(c.base[c.rank] + kLLStateOff);
+      __threadfence_system();
+      if (atomicAdd(ctas, 1u) == gridDim.x - 1) {
+        *ctas = 0;
+        __threadfence_system();
+        *(volatile uint32_t*)done_host = seq;
+      }
+    }
   }
 }
 

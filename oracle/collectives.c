@@ -13,6 +13,9 @@
  *                 address list (/root/reference/network.go:94-109)                        -> concat
  *   Allreduce     the composition a reference user writes from Send/Receive: gather, then
  *                 acc = x_0; acc = op(acc, x_r), r = 1..n-1, in the element type, then Bcast.
+ *   Reduce        the same value, on root only.
+ *   ReduceScatter rank j holds the Allreduce of everyone's block j (n blocks of `count`).
+ *   Alltoall      recv_j[r*count ..] == send_r[j*count ..]: what n*n Send/Receive pairs deliver.
  *
  * PARITY UNPINNED for Bcast/Allreduce/Allgather: the reference has no such functions
  * (/root/reference/mpi.go:130 is a commented stub) and no tests, so there is no golden vector to
@@ -100,6 +103,21 @@ int oracle_allreduce(int dtype, int op, int order, int n, size_t count, const vo
 int oracle_allgather(int dtype, int n, size_t count, const void* const* in, void* out) {
   const size_t b = count * esize(dtype);
   for (int r = 0; r < n; ++r) memcpy((char*)out + (size_t)r * b, in[r], b);
+  return 0;
+}
+
+/* ReduceScatter: in[r] holds n*count elements; out (count elements) is what rank `me` receives */
+int oracle_reduce_scatter(int dtype, int op, int order, int n, int me, size_t count, const void* const* in, void* out) {
+  const void* blk[8];
+  if (n < 1 || n > 8 || me < 0 || me >= n) return -1;
+  for (int r = 0; r < n; ++r) blk[r] = (const char*)in[r] + (size_t)me * count * esize(dtype);
+  return oracle_allreduce(dtype, op, order, n, count, blk, out);
+}
+
+/* Alltoall: in[r] holds n*count elements; out (n*count elements) is what rank `me` receives */
+int oracle_alltoall(int dtype, int n, int me, size_t count, const void* const* in, void* out) {
+  const size_t b = count * esize(dtype);
+  for (int r = 0; r < n; ++r) memcpy((char*)out + (size_t)r * b, (const char*)in[r] + (size_t)me * b, b);
   return 0;
 }
 

@@ -36,6 +36,8 @@ def lib():
         c = ctypes
         L.oracle_allreduce.argtypes = [c.c_int, c.c_int, c.c_int, c.c_int, c.c_size_t, c.POINTER(c.c_void_p), c.c_void_p]
         L.oracle_allgather.argtypes = [c.c_int, c.c_int, c.c_size_t, c.POINTER(c.c_void_p), c.c_void_p]
+        L.oracle_reduce_scatter.argtypes = [c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_size_t, c.POINTER(c.c_void_p), c.c_void_p]
+        L.oracle_alltoall.argtypes = [c.c_int, c.c_int, c.c_int, c.c_size_t, c.POINTER(c.c_void_p), c.c_void_p]
         L.oracle_splitmix64.argtypes = [c.c_uint64, c.c_uint64]
         L.oracle_splitmix64.restype = c.c_uint64
         for f in ("oracle_fill_i64", "oracle_fill_f32", "oracle_fill_f64"):
@@ -90,6 +92,43 @@ def allgather(inputs):
 
 def bcast(root_buf):
     return np.array(root_buf, copy=True)
+
+
+def reduce_scatter(inputs, me, op=SUM, order=ORDER_RANK):
+    """inputs[r] holds n blocks; returns what rank `me` receives (block `me` reduced over ranks)."""
+    n = len(inputs)
+    arrs = [np.ascontiguousarray(a) for a in inputs]
+    dt = arrs[0].dtype
+    count = arrs[0].size // n
+    out = np.empty(count, dtype=dt)
+    ptrs = (ctypes.c_void_p * n)(*[a.ctypes.data for a in arrs])
+    if lib().oracle_reduce_scatter(NP2DT[dt], op, order, n, me, count, ptrs, out.ctypes.data):
+        raise ValueError("oracle_reduce_scatter: bad arguments")
+    return out
+
+
+def alltoall(inputs, me):
+    """inputs[r] holds n blocks; returns what rank `me` receives: block `me` of every rank, in rank order."""
+    n = len(inputs)
+    arrs = [np.ascontiguousarray(a) for a in inputs]
+    dt = arrs[0].dtype
+    count = arrs[0].size // n
+    out = np.empty(count * n, dtype=dt)
+    ptrs = (ctypes.c_void_p * n)(*[a.ctypes.data for a in arrs])
+    lib().oracle_alltoall(NP2DT[dt], n, me, count, ptrs, out.ctypes.data)
+    return out
+
+
+def reduce_scatter_np(inputs, me, op=SUM, order=ORDER_RANK):
+    n = len(inputs)
+    count = np.asarray(inputs[0]).size // n
+    return allreduce_np([np.asarray(a).reshape(-1)[me * count:(me + 1) * count] for a in inputs], op=op, order=order)
+
+
+def alltoall_np(inputs, me):
+    n = len(inputs)
+    count = np.asarray(inputs[0]).size // n
+    return np.concatenate([np.asarray(a).reshape(-1)[me * count:(me + 1) * count] for a in inputs])
 
 
 # ---- numpy twin (independent restatement used to cross-check the C oracle) --------------------

@@ -19,7 +19,7 @@ from oracle import oracle as O  # noqa: E402
 
 SEED = 0xB2000000
 DTYPES = {"f32": np.float32, "f64": np.float64, "i64": np.int64}
-ALGOS = {"auto": 0, "oneshot": 1, "twoshot": 2, "ring": 3, "nvls": 4, "smem": 5, "ll": 6}
+ALGOS = {"auto": 0, "oneshot": 1, "twoshot": 2, "ring": 3, "nvls": 4, "smem": 5, "ll": 6, "hybrid": 7}
 
 
 def inputs_for(dtype, n, count, salt=0):
@@ -33,7 +33,7 @@ def expect_allreduce(ins, op, algo_used, n, count, dtype):
         order = O.ORDER_TREE if (n in (2, 4, 8) and nvec <= 4096) else O.ORDER_RANK
     elif algo_used == L.ALGO_RING:
         order = O.ORDER_RING
-    elif algo_used == L.ALGO_NVLS:
+    elif algo_used in (L.ALGO_NVLS, L.ALGO_HYBRID):
         order = O.ORDER_F64
     else:
         order = O.ORDER_RANK
@@ -96,19 +96,27 @@ def scenario_collectives(a):
     rank, n = mpi.Rank(), mpi.Size()
     sizes = [int(s) for s in a.sizes.split(",")]
     dtypes = a.dtypes.split(",")
-    algos = a.algos.split(",")
     kinds = a.kinds.split(",")
     info = (L.ctypes.c_size_t(), L.ctypes.c_size_t(), L.ctypes.c_int())
     lib.b200mpi_heap_info(L.ctypes.byref(info[0]), L.ctypes.byref(info[1]), L.ctypes.byref(info[2]))
     nvls = bool(info[2].value)
+    # an explicit request for a switch algorithm that cannot run is REPORTED (the test then skips
+    # or fails visibly); the default list only names what this world can run
+    explicit = a.algos != "default"
+    algos = a.algos.split(",") if explicit else ["oneshot", "twoshot", "ring", "smem"] + (["nvls", "hybrid"] if nvls else [])
     done = 0
+    skipped = set()
+    if "hybrid" in algos:
+        lib.b200mpi_set_param(b"hybrid_p2p_permille", 250)
+        lib.b200mpi_set_param(b"hybrid_min_bytes", 0)
     for kind in kinds:
         for dn in dtypes:
             dt = DTYPES[dn]
             for count in sizes:
                 ins = inputs_for(dt, n, count, salt=count % 97)
                 for algo in algos:
-                    if algo == "nvls" and not nvls:
+                    if algo in ("nvls", "hybrid") and not nvls:
+                        skipped.add("allreduce:" + algo)  # reported, never silently passed
                         continue
                     if algo in ("ring", "smem") and n == 1:
                         continue
@@ -137,8 +145,12 @@ def scenario_collectives(a):
                     free_buffer(send)
                     free_buffer(recv)
                     done += 1
-                # allgather: push and ring
-                for algo in ("auto", "ring"):
+                # allgather: push, ring and the switch form
+                for algo in ("oneshot", "ring", "nvls"):
+                    if algo == "nvls" and not nvls:
+                        if explicit and "nvls" in algos:
+                            skipped.add("allgather:nvls")
+                        continue
                     lib.b200mpi_set_algo(L.COLL_ALLGATHER, ALGOS[algo])
                     send = make_buffer(kind, ins[rank])
                     recv = make_buffer(kind, np.full(count * n, -1, dtype=dt))
@@ -150,10 +162,13 @@ def scenario_collectives(a):
                 lib.b200mpi_set_algo(L.COLL_ALLGATHER, 0)
                 # bcast from every root with every algorithm (root 0 and last only for big sizes)
                 roots = range(n) if count <= 4096 else sorted({0, n - 1})
-                for algo in ("oneshot", "twoshot", "nvls"):
-                    if algo == "nvls" and not nvls:
+                for algo in ("oneshot", "twoshot", "nvls", "nvls_root"):
+                    if algo.startswith("nvls") and not nvls:
+                        if explicit and "nvls" in algos:
+                            skipped.add("bcast:" + algo)
                         continue
-                    lib.b200mpi_set_algo(L.COLL_BCAST, ALGOS[algo])
+                    lib.b200mpi_set_param(b"bcast_nvls2", 0 if algo == "nvls_root" else 1)
+                    lib.b200mpi_set_algo(L.COLL_BCAST, ALGOS["nvls" if algo == "nvls_root" else algo])
                     for root in roots:
                         buf = make_buffer(kind, ins[root] if rank == root else np.full(count, -1, dtype=dt).astype(dt))
                         mpi.Bcast(buf, root)
@@ -162,7 +177,225 @@ def scenario_collectives(a):
                         done += 1
                 lib.b200mpi_set_algo(L.COLL_BCAST, 0)
     mpi.Barrier()
-    return {"checked": done, "nvls": nvls}
+    return {"checked": done, "nvls": nvls, "nvls_skipped": bool(skipped), "skipped": sorted(skipped)}
+
+
+def pinned_array(count, dtype):
+    """numpy view of pinned host memory from b200mpi_host_alloc (on the GPU's NUMA node)."""
+    import ctypes
+    dt = np.dtype(dtype)
+    p = ctypes.c_void_p()
+    if L.load().b200mpi_host_alloc(max(count * dt.itemsize, 1), ctypes.byref(p)):
+        raise RuntimeError(L.last_error())
+    buf = (ctypes.c_char * max(count * dt.itemsize, 1)).from_address(p.value)
+    return np.frombuffer(buf, dtype=dt, count=count), p
+
+
+def scenario_newcolls(a):
+    """ReduceScatter, Reduce, Alltoall (API added along the reference's conventions) against the oracle."""
+    lib = L.load()
+    rank, n = mpi.Rank(), mpi.Size()
+    sizes = [int(s) for s in a.sizes.split(",")]
+    info = (L.ctypes.c_size_t(), L.ctypes.c_size_t(), L.ctypes.c_int())
+    lib.b200mpi_heap_info(L.ctypes.byref(info[0]), L.ctypes.byref(info[1]), L.ctypes.byref(info[2]))
+    nvls = bool(info[2].value)
+    done, skipped = 0, set()
+    for kind in a.kinds.split(","):
+        for dn in a.dtypes.split(","):
+            dt = DTYPES[dn]
+            for count in sizes:
+                ins = inputs_for(dt, n, count * n, salt=count % 89 + 3)  # n blocks of `count` per rank
+                # ---- ReduceScatter
+                for algo in ("twoshot", "nvls"):
+                    if algo == "nvls" and not nvls:
+                        skipped.add("reduce_scatter:nvls")
+                        continue
+                    lib.b200mpi_set_algo(L.COLL_REDUCE_SCATTER, ALGOS[algo])
+                    for op, oop in ((mpi.SUM, O.SUM), (mpi.MAX, O.MAX)):
+                        send = make_buffer(kind, ins[rank])
+                        recv = make_buffer(kind, np.zeros(count, dtype=dt))
+                        mpi.ReduceScatter(send, recv, op)
+                        exact = dt == np.int64 or algo != "nvls" or op != mpi.SUM
+                        want = O.reduce_scatter(ins, rank, op=oop, order=O.ORDER_RANK if exact else O.ORDER_F64)
+                        blocks = [x[rank * count:(rank + 1) * count] for x in ins]
+                        check_equal(read_buffer(recv), want, "reduce_scatter %s %s count=%d algo=%s op=%d" % (kind, dn, count, algo, op), exact=exact, ins=blocks)
+                        check_equal(read_buffer(send), ins[rank], "reduce_scatter send untouched")
+                        free_buffer(send)
+                        free_buffer(recv)
+                        done += 1
+                    if kind == "heap":  # in place: recv is the caller's own block of send
+                        send = make_buffer(kind, ins[rank])
+                        mpi.ReduceScatter(send, send[rank * count:(rank + 1) * count], mpi.SUM)
+                        exact = dt == np.int64 or algo != "nvls"
+                        want = O.reduce_scatter(ins, rank, order=O.ORDER_RANK if exact else O.ORDER_F64)
+                        check_equal(send.to_host()[rank * count:(rank + 1) * count], want, "reduce_scatter in place %s count=%d algo=%s" % (dn, count, algo), exact=exact,
+                                    ins=[x[rank * count:(rank + 1) * count] for x in ins])
+                        free_buffer(send)
+                        done += 1
+                lib.b200mpi_set_algo(L.COLL_REDUCE_SCATTER, 0)
+                # ---- Reduce to every root (small) or to {0, n-1}
+                red = [x[:count] for x in ins]
+                roots = range(n) if count <= 4096 else sorted({0, n - 1})
+                for algo in ("twoshot", "auto"):
+                    lib.b200mpi_set_algo(L.COLL_ALLREDUCE, ALGOS[algo])
+                    for root in roots:
+                        send = make_buffer(kind, red[rank])
+                        recv = make_buffer(kind, np.full(count, -7, dtype=dt))
+                        mpi.Reduce(send, recv, mpi.SUM, root)
+                        got = read_buffer(recv)
+                        if rank == root:
+                            exact = dt == np.int64 or algo == "twoshot" or not nvls or n < 4
+                            check_equal(got, O.allreduce(red, order=O.ORDER_RANK if exact else O.ORDER_F64), "reduce %s %s count=%d root=%d algo=%s" % (kind, dn, count, root, algo), exact=exact, ins=red)
+                        else:
+                            check_equal(got, np.full(count, -7, dtype=dt), "reduce: non-root recv untouched")
+                        free_buffer(send)
+                        free_buffer(recv)
+                        done += 1
+                lib.b200mpi_set_algo(L.COLL_ALLREDUCE, 0)
+                # ---- Alltoall
+                send = make_buffer(kind, ins[rank])
+                recv = make_buffer(kind, np.full(count * n, -1, dtype=dt))
+                mpi.Alltoall(send, recv)
+                check_equal(read_buffer(recv), O.alltoall(ins, rank), "alltoall %s %s count=%d" % (kind, dn, count))
+                free_buffer(send)
+                free_buffer(recv)
+                done += 1
+    mpi.Barrier()
+    return {"checked": done, "nvls": nvls, "nvls_skipped": bool(skipped), "skipped": sorted(skipped)}
+
+
+def scenario_hostpipe(a):
+    """Host slices through the chunked H2D | collective | D2H pipeline: pageable memory (pinned
+    bounce ring + helper threads) and pinned memory (direct DMA), several chunks per call."""
+    lib = L.load()
+    rank, n = mpi.Rank(), mpi.Size()
+    for k, v in (("pipe_min_bytes", 65536), ("pipe_chunk_bytes", 65536), ("bounce_chunk_bytes", 65536)):
+        if lib.b200mpi_set_param(k.encode(), v):
+            raise RuntimeError(L.last_error())
+    done = 0
+    frees = []
+    for dn in a.dtypes.split(","):
+        dt = DTYPES[dn]
+        for count in [int(s) for s in a.sizes.split(",")]:
+            ins = inputs_for(dt, n, count, salt=count % 83 + 11)
+            for mem in ("pageable", "pinned"):
+                def host(arr):
+                    if mem == "pageable":
+                        return np.array(arr, copy=True)
+                    v, p = pinned_array(arr.size, arr.dtype)
+                    frees.append(p)
+                    v[:] = arr
+                    return v
+                # allreduce, out of place and in place
+                send, recv = host(ins[rank]), host(np.zeros(count, dtype=dt))
+                mpi.Allreduce(send, recv)
+                used = lib.b200mpi_get_algo(L.COLL_ALLREDUCE, min(count, 65536 // dt().itemsize), O.NP2DT[np.dtype(dt)]) if n > 1 else L.ALGO_TWOSHOT
+                exact = dt == np.int64 or used not in (L.ALGO_NVLS, L.ALGO_HYBRID)
+                want = O.allreduce(ins, order=O.ORDER_F64) if not exact else None
+                if exact:  # chunks of 64 KiB: small-message algorithms, tree order below 4096 vectors
+                    want = np.empty(count, dtype=dt)
+                    ce = max(65536 // dt().itemsize, 4096) // 4096 * 4096
+                    for lo in range(0, count, ce):
+                        part = [x[lo:lo + ce] for x in ins]
+                        want[lo:lo + ce], _ = expect_allreduce(part, O.SUM, lib.b200mpi_get_algo(L.COLL_ALLREDUCE, len(part[0]), O.NP2DT[np.dtype(dt)]) if n > 1 else L.ALGO_TWOSHOT, n, len(part[0]), dt)
+                check_equal(recv, want, "hostpipe allreduce %s %s count=%d" % (mem, dn, count), exact=exact, ins=ins)
+                check_equal(send, ins[rank], "hostpipe allreduce send untouched")
+                mpi.Allreduce(send, send)
+                check_equal(send, want, "hostpipe allreduce in place %s %s count=%d" % (mem, dn, count), exact=exact, ins=ins)
+                done += 2
+                # bcast from first and last rank
+                for root in sorted({0, n - 1}):
+                    buf = host(ins[root] if rank == root else np.full(count, -3, dtype=dt))
+                    mpi.Bcast(buf, root)
+                    check_equal(buf, ins[root], "hostpipe bcast %s %s count=%d root=%d" % (mem, dn, count, root))
+                    done += 1
+                # allgather
+                send, recv = host(ins[rank]), host(np.full(count * n, -1, dtype=dt))
+                mpi.Allgather(send, recv)
+                check_equal(recv, O.allgather(ins), "hostpipe allgather %s %s count=%d" % (mem, dn, count))
+                done += 1
+    for p in frees:
+        lib.b200mpi_host_free(p)
+    mpi.Barrier()
+    return {"checked": done, "numa_node": lib.b200mpi_numa_node()}
+
+
+def scenario_isend(a):
+    """Isend/Wait (mpi.go:132-152): the buffer is reusable right after Isend; Wait frees the tag."""
+    rank, n = mpi.Rank(), mpi.Size()
+    peer = rank ^ 1
+    done = 0
+    for kind in ("host", "heap"):
+        for count in (0, 1, 1000, 300000):
+            x = O.fill(np.float64, SEED + rank + count, count)
+            buf = make_buffer(kind, x)
+            if rank % 2 == 0:
+                mpi.Isend(buf, peer, 4)
+                # the data left the buffer: scribble over it before the peer has received
+                if kind == "host":
+                    buf[:] = -1.0
+                else:
+                    buf.copy_from_host(np.full(count, -1.0))
+                try:
+                    mpi.Isend(x, peer, 4)
+                    raise AssertionError("tag reusable before Wait")
+                except mpi.TagExists:
+                    pass
+                mpi.Send(np.arange(3, dtype=np.int64), peer, 5)  # a second message overtakes nothing: tags differ
+                mpi.Wait(peer, 4)
+                mpi.Isend(x, peer, 4)  # pair is free again
+                mpi.Wait(peer, 4)
+            else:
+                mpi.Receive(np.zeros(3, dtype=np.int64), peer, 5)
+                got = mpi.Receive(make_buffer(kind, np.zeros(count)), peer, 4)
+                check_equal(read_buffer(got), O.fill(np.float64, SEED + peer + count, count), "isend %s count=%d" % (kind, count))
+                got2 = mpi.Receive(np.zeros(count), peer, 4)
+                check_equal(got2, O.fill(np.float64, SEED + peer + count, count), "isend again %s count=%d" % (kind, count))
+            free_buffer(buf)
+            done += 1
+    try:
+        mpi.Wait(peer, 77)
+        raise AssertionError("Wait without Isend succeeded")
+    except mpi.MpiError as e:
+        if e.code != L.ERR_ARG:
+            raise
+    mpi.Barrier()
+    return {"checked": done}
+
+
+def scenario_sendtimeout(a):
+    """A Send that times out withdraws its post: a late Receive must not match it, the staging block
+    and the mailbox slot are reusable (run with a short B200MPI_WATCHDOG_S)."""
+    import time
+    rank, n = mpi.Rank(), mpi.Size()
+    lib = L.load()
+    x = O.fill(np.int64, SEED + 9, 5000)
+    used0 = L.ctypes.c_size_t()
+    lib.b200mpi_heap_info(None, L.ctypes.byref(used0), None)
+    if rank == 0:
+        lib.b200mpi_set_param(b"watchdog_ms", 700)
+        for _ in range(3):
+            try:
+                mpi.Send(x, 1, 21)
+                raise AssertionError("send without receiver succeeded")
+            except mpi.MpiError as e:
+                if e.code != L.ERR_TIMEOUT:
+                    raise
+        used1 = L.ctypes.c_size_t()
+        lib.b200mpi_heap_info(None, L.ctypes.byref(used1), None)
+        if used1.value != used0.value:
+            raise AssertionError("staging leaked after timeouts: %d -> %d" % (used0.value, used1.value))
+        lib.b200mpi_set_param(b"watchdog_ms", 120000)
+        mpi.Send(np.arange(2, dtype=np.int64), 1, 22)  # go
+        for i in range(40):  # more than the 16 slots of the pair
+            mpi.Send(x + i, 1, 21)
+    elif rank == 1:
+        mpi.Receive(np.zeros(2, dtype=np.int64), 0, 22)
+        for i in range(40):
+            got = mpi.Receive(np.zeros(5000, dtype=np.int64), 0, 21)
+            check_equal(got, x + i, "message %d after withdrawn posts" % i)
+    mpi.Barrier()
+    return {"checked": 41}
 
 
 def scenario_edge_values(a):
@@ -628,7 +861,7 @@ def main():
     ap.add_argument("--out", required=True)
     ap.add_argument("--sizes", default="0,1,3,4,5,255,256,257,4096,65537")
     ap.add_argument("--dtypes", default="f32,f64,i64")
-    ap.add_argument("--algos", default="oneshot,twoshot,ring,nvls,smem")
+    ap.add_argument("--algos", default="default", help="default: every P2P algorithm, plus the switch forms where a multicast mapping exists")
     ap.add_argument("--kinds", default="heap,host")
     ap.add_argument("--gpu", type=int, default=None)
     ap.add_argument("--what", default="allgather")

@@ -30,6 +30,18 @@ def world(n, scenario, *args, timeout=420, env=None):
     return res
 
 
+def need_gpus(k, what):
+    have = ngpus()
+    if have < k:
+        pytest.skip("%s needs >= %d GPUs with NVLink/NVLS between them; this box has %d (ranks sharing one GPU cannot bind a multicast object)" % (what, k, have))
+    return have
+
+
+def assert_nothing_skipped(results):
+    sk = sorted({x for r in results for x in r.get("skipped", [])})
+    assert not sk, "the switch paths did not run: %s" % sk
+
+
 def test_smoke_world_of_1_and_2():
     r1 = world(1, "smoke")
     assert r1[0]["device"] == 0
@@ -90,9 +102,46 @@ def test_mismatched_collectives_are_reported_not_hung():
 
 
 @pytest.mark.parametrize("n", [2, 4])
-def test_ll_allreduce_experimental(n):
-    """Barrier-free LL allreduce (<= 32 KiB, off by default): rank-order results, bit-exact."""
-    world(n, "collectives", "--algos", "ll", "--sizes", "0,1,2,3,257,4097,8192", "--kinds", "heap,host")
+def test_ll_allreduce(n):
+    """Barrier-free LL allreduce (the small-message default on real multi-GPU worlds): rank-order
+    results, bit-exact; device pointers and host slices (mapped pinned bounce, one kernel)."""
+    world(n, "collectives", "--algos", "ll", "--sizes", "0,1,2,3,257,4097,8192,40000", "--kinds", "heap,host")
+
+
+@pytest.mark.parametrize("n", [2, 3, 4])
+def test_reduce_scatter_reduce_alltoall(n):
+    world(n, "newcolls", "--sizes", "0,1,5,257,4099,70001")
+
+
+def test_reduce_scatter_reduce_alltoall_world_of_8():
+    world(8, "newcolls", "--sizes", "3,4099", "--kinds", "heap", "--dtypes", "f32,i64", timeout=600)
+
+
+@pytest.mark.parametrize("n", [1, 2, 4])
+def test_host_slice_pipeline_pageable_and_pinned(n):
+    world(n, "hostpipe", "--sizes", "16385,300001", "--dtypes", "f32,i64" if n == 4 else "f32,f64,i64")
+
+
+def test_isend_wait():
+    world(2, "isend")
+    world(4, "isend")
+
+
+def test_send_timeout_withdraws_the_post():
+    world(2, "sendtimeout")
+
+
+def test_switch_paths_on_real_nvlink():
+    """NVLS / hybrid allreduce, NVLS allgather, bcast and reduce-scatter, and LL over real NVLink.
+    They cannot run when ranks share one GPU: shown as SKIPPED there, never as passed."""
+    have = need_gpus(2, "multimem (NVLS) kernels")
+    n = 8 if have >= 8 else 4 if have >= 4 else 2
+    res = world(n, "collectives", "--algos", "nvls,hybrid,ll", "--sizes", "1,257,4096,40001,1048577", "--kinds", "heap", timeout=900,
+                env={"B200MPI_HEAP_BYTES": str(512 << 20)})
+    assert all(r["nvls"] for r in res), "multicast mapping was not set up on a multi-GPU box"
+    assert_nothing_skipped(res)
+    res = world(n, "newcolls", "--sizes", "1,4099,262144", "--kinds", "heap", timeout=900, env={"B200MPI_HEAP_BYTES": str(512 << 20)})
+    assert_nothing_skipped(res)
 
 
 def test_full_size_points():
