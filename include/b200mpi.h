@@ -166,12 +166,20 @@ int b200mpi_set_max_blocks(int blocks); /* cap grid size (0 = default: SMs x occ
  * "hybrid_p2p_permille", "hybrid_p2p_blocks", "hybrid_min_bytes", "bcast_nvls2", "bcast_nvls_min",
  * "allgather_nvls_min". */
 int b200mpi_set_param(const char* name, int64_t value);
+int b200mpi_get_param(const char* name, int64_t* value); /* also "sm_count", "shared_device" (read only) */
 /* cudaStream_t used for collectives; set NULL to restore the library's own stream. */
 int b200mpi_get_stream(void** stream);
 int b200mpi_set_stream(void* stream);
 /* CUDA-event stopwatch on the collective stream. */
 int b200mpi_timer_start(void);
 int b200mpi_timer_stop(float* ms); /* synchronises; elapsed since timer_start */
+/* Measured bound of the host-slice paths: pinned host <-> device-heap copy rates of this rank's GPU,
+ * GB/s (1e9): H2D alone, D2H alone, and per direction with both running at once. */
+int b200mpi_pcie_probe(size_t bytes, int iters, double* h2d_gbs, double* d2h_gbs, double* bidir_gbs);
+/* Raw NVLink rates of the library's copy kernel between neighbouring ranks (collective call).
+ * mode 0: every rank pulls `bytes` from rank+1; 1: every rank pushes to rank+1; 2 / 3: only rank 0
+ * pulls from / pushes to rank 1; 4: every rank pulls and pushes at once.  *ms: device time per iteration. */
+int b200mpi_link_probe(size_t bytes, int mode, int iters, float* ms);
 /* Number of kernels this library has launched since init. */
 int64_t b200mpi_launch_count(void);
 

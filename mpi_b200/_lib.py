@@ -58,10 +58,13 @@ SYMBOLS = {
     "b200mpi_get_algo": (_c.c_int, [_c.c_int, _c.c_size_t, _c.c_int]),
     "b200mpi_set_max_blocks": (_c.c_int, [_c.c_int]),
     "b200mpi_set_param": (_c.c_int, [_c.c_char_p, _c.c_int64]),
+    "b200mpi_get_param": (_c.c_int, [_c.c_char_p, _c.POINTER(_c.c_int64)]),
     "b200mpi_get_stream": (_c.c_int, [_c.POINTER(_c.c_void_p)]),
     "b200mpi_set_stream": (_c.c_int, [_c.c_void_p]),
     "b200mpi_timer_start": (_c.c_int, []),
     "b200mpi_timer_stop": (_c.c_int, [_c.POINTER(_c.c_float)]),
+    "b200mpi_pcie_probe": (_c.c_int, [_c.c_size_t, _c.c_int, _c.POINTER(_c.c_double), _c.POINTER(_c.c_double), _c.POINTER(_c.c_double)]),
+    "b200mpi_link_probe": (_c.c_int, [_c.c_size_t, _c.c_int, _c.c_int, _c.POINTER(_c.c_float)]),
     "b200mpi_launch_count": (_c.c_int64, []),
 }
 
@@ -84,6 +87,13 @@ def load():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+def get_param(name):
+    v = ctypes.c_int64()
+    if load().b200mpi_get_param(name.encode(), ctypes.byref(v)):
+        raise RuntimeError(last_error())
+    return v.value
 
 
 def last_error():

@@ -1776,6 +1776,104 @@ int b200mpi_memcpy(void* dst, const void* src, size_t bytes, int kind) {
   CUDA_OK(cudaStreamSynchronize(g->stream));
   return 0;
 }
+// Measured bound of the host-slice paths: plain pinned copies between a NUMA-local pinned buffer and
+// the device heap, no collective.  bidir = H2D and D2H of `bytes` each running at the same time
+// (what a pipelined host-slice Allreduce needs), reported per direction.
+int b200mpi_pcie_probe(size_t bytes, int iters, double* h2d_gbs, double* d2h_gbs, double* bidir_gbs) {
+  int rc = need_data_plane();
+  if (rc) return rc;
+  if (bytes == 0 || iters < 1) return fail(B200MPI_ERR_ARG, "pcie_probe: bytes and iters must be positive");
+  void *ha = nullptr, *hb = nullptr;
+  if ((rc = numa_host_alloc(bytes, &ha)) || (rc = numa_host_alloc(bytes, &hb))) { if (ha) cudaFreeHost(ha); return rc; }
+  memset(ha, 1, bytes);
+  size_t oa = 0, ob = 0;
+  if (g->heap.alloc(bytes, oa) || g->heap.alloc(bytes, ob)) {
+    cudaFreeHost(ha); cudaFreeHost(hb);
+    return fail(B200MPI_ERR_NOMEM, "pcie_probe: symmetric heap exhausted");
+  }
+  char* da = (char*)g->heap.base[g->ctrl.rank] + oa;
+  char* db = (char*)g->heap.base[g->ctrl.rank] + ob;
+  auto timed = [&](bool up, bool down) {
+    cudaStreamSynchronize(g->h2d_stream);
+    cudaStreamSynchronize(g->d2h_stream);
+    const auto t0 = Clock::now();
+    for (int i = 0; i < iters; ++i) {
+      if (up) cudaMemcpyAsync(da, ha, bytes, cudaMemcpyHostToDevice, g->h2d_stream);
+      if (down) cudaMemcpyAsync(hb, db, bytes, cudaMemcpyDeviceToHost, g->d2h_stream);
+    }
+    cudaStreamSynchronize(g->h2d_stream);
+    cudaStreamSynchronize(g->d2h_stream);
+    const double sec = std::chrono::duration<double>(Clock::now() - t0).count();
+    return (double)bytes * iters / sec / 1e9;
+  };
+  timed(true, true); // warm-up
+  const double up = timed(true, false), down = timed(false, true), both = timed(true, true);
+  if (h2d_gbs) *h2d_gbs = up;
+  if (d2h_gbs) *d2h_gbs = down;
+  if (bidir_gbs) *bidir_gbs = both;
+  g->heap.free_off(oa);
+  g->heap.free_off(ob);
+  cudaFreeHost(ha);
+  cudaFreeHost(hb);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(B200MPI_ERR_CUDA, std::string("pcie_probe: ") + cudaGetErrorString(e));
+  return 0;
+}
+// Raw NVLink rates seen by this library's copy kernel between neighbouring ranks (the roofline the
+// P2P collectives are held against).  Collective call.  mode 0: every rank pulls `bytes` from rank+1;
+// 1: every rank pushes to rank+1; 2: only rank 0 pulls from rank 1; 3: only rank 0 pushes to rank 1;
+// 4: every rank pulls from and pushes to rank+1 at the same time (two streams).
+// *ms = device time of one iteration on this rank (0 for idle ranks).
+int b200mpi_link_probe(size_t bytes, int mode, int iters, float* ms) {
+  int rc = need_data_plane();
+  if (rc) return rc;
+  const int n = g->ctrl.n, me = g->ctrl.rank;
+  if (n < 2 || bytes == 0 || iters < 1 || mode < 0 || mode > 4 || !ms) return fail(B200MPI_ERR_ARG, "link_probe: needs >= 2 ranks, bytes, iters >= 1, mode 0..4");
+  size_t a = 0, b = 0;
+  if (g->heap.alloc(bytes, a) || g->heap.alloc(bytes, b)) return fail(B200MPI_ERR_NOMEM, "link_probe: symmetric heap exhausted");
+  struct Offs { uint64_t a, b; } mine = {a, b}, all[B200MPI_MAX_RANKS];
+  std::string err;
+  if ((rc = g->ctrl.allgather(&mine, sizeof mine, all, err))) return fail(rc, err);
+  const int peer = (me + 1) % n;
+  char* my_a = (char*)g->heap.base[me] + a;
+  char* my_b = (char*)g->heap.base[me] + b;
+  char* peer_a = (char*)g->heap.base[peer] + all[peer].a;
+  char* peer_b = (char*)g->heap.base[peer] + all[peer].b;
+  const bool active = mode == 0 || mode == 1 || mode == 4 || me == 0;
+  cudaStream_t s2 = g->h2d_stream;
+  CUDA_OK(cudaStreamSynchronize(g->stream));
+  if ((rc = g->ctrl.barrier(err))) return fail(rc, err);
+  *ms = 0.f;
+  if (active) {
+    for (int pass = 0; pass < 2; ++pass) { // pass 0 warms up
+      const int k = pass ? iters : 2;
+      CUDA_OK(cudaEventRecord(g->ev0, g->stream));
+      if (mode == 4) CUDA_OK(cudaStreamWaitEvent(s2, g->ev0, 0));
+      for (int i = 0; i < k && rc == 0; ++i) {
+        if (mode == 0 || mode == 2 || mode == 4) rc = launch_copy(my_a, peer_a, bytes, g->stream);          // pull: loads cross the link
+        if (rc == 0 && (mode == 1 || mode == 3)) rc = launch_copy(peer_b, my_b, bytes, g->stream);           // push: stores cross the link
+        if (rc == 0 && mode == 4) rc = launch_copy(peer_b, my_b, bytes, s2);
+      }
+      if (rc) break;
+      if (mode == 4) {
+        cudaEvent_t e = g->pipe_events.empty() ? nullptr : g->pipe_events[0];
+        if (!e) { CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); g->pipe_events.push_back(e); }
+        CUDA_OK(cudaEventRecord(e, s2));
+        CUDA_OK(cudaStreamWaitEvent(g->stream, e, 0));
+      }
+      CUDA_OK(cudaEventRecord(g->ev1, g->stream));
+      CUDA_OK(cudaEventSynchronize(g->ev1));
+      float t = 0;
+      CUDA_OK(cudaEventElapsedTime(&t, g->ev0, g->ev1));
+      *ms = t / k;
+    }
+  }
+  std::string err2;
+  g->ctrl.barrier(err2); // nobody frees while a neighbour still copies
+  g->heap.free_off(a);
+  g->heap.free_off(b);
+  return rc;
+}
 int b200mpi_numa_node(void) { return (g && g->initialised && !g->control_only) ? g->gpu_numa_node : -1; }
 int b200mpi_heap_info(size_t* total, size_t* used, int* nvls) {
   int rc = need_data_plane();
@@ -1866,6 +1964,35 @@ int b200mpi_set_param(const char* name, int64_t value) {
   else if (k == "bounce_chunk_bytes") g->bounce_chunk_bytes = (size_t)std::max<int64_t>(value, 65536);
   else if (k == "host_threads") { if (g->pool.running()) return fail(B200MPI_ERR_ARG, "set_param: host_threads must be set before the first pageable host-slice call"); g->host_threads = (int)std::max<int64_t>(value, 0); }
   else return fail(B200MPI_ERR_ARG, "set_param: unknown parameter '" + k + "'");
+  return 0;
+}
+int b200mpi_get_param(const char* name, int64_t* value) {
+  if (!g || !g->initialised) return fail(B200MPI_ERR_NOT_INIT, "mpi: Init has not been called");
+  if (!value) return fail(B200MPI_ERR_ARG, "get_param: NULL result pointer");
+  const std::string k = name ? name : "";
+  if (k == "twoshot_unroll") *value = g->twoshot_unroll;
+  else if (k == "nvls_unroll") *value = g->nvls_unroll;
+  else if (k == "nvls_min_ranks") *value = g->nvls_min_ranks;
+  else if (k == "nvls_max_blocks") *value = g->nvls_max_blocks;
+  else if (k == "copy_variant") *value = g->copy_variant;
+  else if (k == "ll_max_bytes") *value = (int64_t)g->ll_max_bytes;
+  else if (k == "oneshot_max_bytes") *value = (int64_t)g->oneshot_max_bytes;
+  else if (k == "pipe_min_bytes") *value = (int64_t)g->pipe_min_bytes;
+  else if (k == "pipe_chunk_bytes") *value = (int64_t)g->pipe_chunk_bytes;
+  else if (k == "bounce_chunk_bytes") *value = (int64_t)g->bounce_chunk_bytes;
+  else if (k == "host_threads") *value = g->host_threads;
+  else if (k == "own_block_bytes") *value = (int64_t)g->own_block_bytes;
+  else if (k == "stage_chunk") *value = (int64_t)g->stage_chunk;
+  else if (k == "watchdog_ms") *value = g->watchdog_ns / 1000000ll;
+  else if (k == "hybrid_p2p_permille") *value = g->hybrid_p2p_permille;
+  else if (k == "hybrid_p2p_blocks") *value = g->hybrid_p2p_blocks;
+  else if (k == "hybrid_min_bytes") *value = (int64_t)g->hybrid_min_bytes;
+  else if (k == "bcast_nvls2") *value = g->bcast_nvls2;
+  else if (k == "bcast_nvls_min") *value = (int64_t)g->bcast_nvls_min;
+  else if (k == "allgather_nvls_min") *value = (int64_t)g->allgather_nvls_min;
+  else if (k == "sm_count") *value = g->sm_count;
+  else if (k == "shared_device") *value = g->shared_device ? 1 : 0;
+  else return fail(B200MPI_ERR_ARG, "get_param: unknown parameter '" + k + "'");
   return 0;
 }
 int b200mpi_set_max_blocks(int blocks) {

@@ -141,6 +141,16 @@ uint64_t oracle_splitmix64(uint64_t seed, uint64_t i) {
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   return z ^ (z >> 31);
 }
+/* the same streams from element `start` on: large buffers are generated and checked block by block */
+void oracle_fill_i64_at(uint64_t seed, size_t start, size_t count, int64_t* out) {
+  for (size_t i = 0; i < count; ++i) out[i] = (int64_t)oracle_splitmix64(seed, start + i);
+}
+void oracle_fill_f32_at(uint64_t seed, size_t start, size_t count, float* out) {
+  for (size_t i = 0; i < count; ++i) out[i] = (float)(oracle_splitmix64(seed, start + i) >> 40) * (1.0f / 16777216.0f);
+}
+void oracle_fill_f64_at(uint64_t seed, size_t start, size_t count, double* out) {
+  for (size_t i = 0; i < count; ++i) out[i] = (double)(oracle_splitmix64(seed, start + i) >> 11) * (1.0 / 9007199254740992.0);
+}
 void oracle_fill_i64(uint64_t seed, size_t count, int64_t* out) {
   for (size_t i = 0; i < count; ++i) out[i] = (int64_t)oracle_splitmix64(seed, i);
 }

@@ -43,6 +43,9 @@ def lib():
         for f in ("oracle_fill_i64", "oracle_fill_f32", "oracle_fill_f64"):
             getattr(L, f).argtypes = [c.c_uint64, c.c_size_t, c.c_void_p]
             getattr(L, f).restype = None
+        for f in ("oracle_fill_i64_at", "oracle_fill_f32_at", "oracle_fill_f64_at"):
+            getattr(L, f).argtypes = [c.c_uint64, c.c_size_t, c.c_size_t, c.c_void_p]
+            getattr(L, f).restype = None
         for f in ("gob_put_uint", "gob_put_int", "gob_put_float"):
             getattr(L, f).restype = c.c_size_t
         L.gob_put_uint.argtypes = [c.c_void_p, c.c_uint64]
@@ -70,6 +73,15 @@ def fill(dtype, seed, count):
     out = np.empty(count, dtype=dt)
     fn = {I64: "oracle_fill_i64", F32: "oracle_fill_f32", F64: "oracle_fill_f64"}[NP2DT[dt]]
     getattr(lib(), fn)(ctypes.c_uint64(seed & (2**64 - 1)), count, out.ctypes.data)
+    return out
+
+
+def fill_at(dtype, seed, start, count):
+    """Elements [start, start+count) of fill(dtype, seed, .): block-wise checks of large buffers."""
+    dt = np.dtype(dtype)
+    out = np.empty(count, dtype=dt)
+    fn = {I64: "oracle_fill_i64_at", F32: "oracle_fill_f32_at", F64: "oracle_fill_f64_at"}[NP2DT[dt]]
+    getattr(lib(), fn)(ctypes.c_uint64(seed & (2**64 - 1)), start, count, out.ctypes.data)
     return out
 
 

@@ -400,14 +400,14 @@ static void* bench_main(void* arg) {
   const size_t total = j->coll == COLL_ALLGATHER ? j->count * n : j->count;
   void* buf = malloc(total * es + 16);
   void* tmp = malloc(j->count * es + 16);
-  double t0 = 0;
+  double t0 = 0, timed = 0;
   for (int it = 0; it < j->warmup + j->iters; ++it) {
     /* fresh inputs every iteration (outside the timed region) */
     if (j->coll == COLL_ALLGATHER) fill_input(j->dtype, j->seed + j->rank, j->count, (char*)buf + (size_t)j->rank * j->count * es);
     else if (j->coll == COLL_BCAST) { if (j->rank == 0) fill_input(j->dtype, j->seed, j->count, buf); else memset(buf, 0xff, j->count * es); }
     else fill_input(j->dtype, j->seed + j->rank, j->count, buf);
     pthread_barrier_wait(j->bar);
-    if (it == j->warmup && j->rank == 0) t0 = now_s();
+    if (j->rank == 0) t0 = now_s();
     int rc = 0;
     switch (j->coll) {
       case COLL_ALLREDUCE: rc = ref_allreduce_ring(c, buf, j->count, j->dtype, tmp); break;
@@ -423,10 +423,11 @@ static void* bench_main(void* arg) {
       }
     }
     if (rc) j->rc = rc;
+    pthread_barrier_wait(j->bar); /* every rank has finished the step: max over ranks */
+    if (j->rank == 0 && it >= j->warmup) timed += now_s() - t0; /* input generation stays outside */
   }
-  pthread_barrier_wait(j->bar);
   if (j->rank == 0) {
-    *j->seconds = (now_s() - t0) / (j->iters > 0 ? j->iters : 1);
+    *j->seconds = timed / (j->iters > 0 ? j->iters : 1);
     if (j->out0) memcpy(j->out0, j->coll == COLL_PINGPONG ? tmp : buf, total * es);
   }
   free(buf); free(tmp);
@@ -434,8 +435,9 @@ static void* bench_main(void* arg) {
 }
 
 /* Runs `warmup`+`iters` iterations of one collective over a fresh world of n ranks with the same
- * synthetic inputs the GPU bench uses (seed + rank).  seconds_per_iter is wall clock from the
- * barrier before the first timed iteration to the barrier after the last (= max over ranks).
+ * synthetic inputs the GPU bench uses (seed + rank).  seconds_per_iter is the mean over the timed
+ * iterations of the wall clock between the barrier before and the barrier after the step
+ * (= max over ranks); regenerating the inputs is not timed.
  * out_rank0 (optional) receives rank 0's final buffer for the parity check.  Returns 0 on success. */
 int ref_bench(int coll, int dtype, int n, size_t count, int iters, int warmup, uint64_t seed, double* seconds_per_iter, void* out_rank0) {
   world* w = ref_world_create(n);

@@ -63,7 +63,7 @@ def main():
         params[k] = int(v)
         if lib.b200mpi_set_param(k.encode(), int(v)):
             raise RuntimeError(L.last_error())
-    ALGOS = {"auto": 0, "oneshot": 1, "twoshot": 2, "ring": 3, "nvls": 4, "smem": 5}
+    ALGOS = {"auto": 0, "oneshot": 1, "twoshot": 2, "ring": 3, "nvls": 4, "smem": 5, "ll": 6, "hybrid": 7}
 
     def emit(d):
         if rank == 0:
@@ -117,7 +117,7 @@ def main():
             if lib.b200mpi_set_param(k.encode(), int(v)):
                 raise RuntimeError(L.last_error())
           for algo in args.algos.split(","):
-              if algo == "nvls" and not nvls:
+              if algo in ("nvls", "hybrid") and not nvls:
                   continue
               if n == 1 and algo != "twoshot":
                   continue
@@ -126,6 +126,10 @@ def main():
                   lib.b200mpi_set_max_blocks(nb)
                   for S in sizes:
                       if algo == "oneshot" and S > (8 << 20):
+                          continue
+                      if algo == "ll" and S > (256 << 10):
+                          continue
+                      if algo == "hybrid" and S < (1 << 20):
                           continue
                       cnt = S // 4
                       it, wm = iters_for(S)
@@ -137,11 +141,25 @@ def main():
                       probe = np.concatenate([recv[:min(cnt, 64)].to_host(), recv[max(cnt - 64, 0):cnt].to_host(), recv[cnt // 2:cnt // 2 + 1].to_host()])
                       ok = bool(np.all(probe == want))
                       emit({"coll": "allreduce", "dtype": "f32", "algo": algo, "bytes": S, "t_us": t * 1e6, "t_call_us": tc * 1e6,
-                            "algbw_gbs": S / t / 1e9, "busbw_gbs": S / t / 1e9 * (2 * (n - 1) / n if n > 1 else 1), "ok": ok, "max_blocks": nb, "pset": dict(ps)})
+                            "algbw_gbs": S / t / 1e9, "busbw_gbs": S / t / 1e9 * (2 * (n - 1) / n if n > 1 else 1), "ok": ok, "max_blocks": nb, "pset": dict(ps),
+                            "algo_used": L.ALGO_NAMES.get(lib.b200mpi_get_algo(L.COLL_ALLREDUCE, cnt, L.F32))})
         lib.b200mpi_set_algo(L.COLL_ALLREDUCE, 0)
         lib.b200mpi_set_max_blocks(0)
         send.free()
         recv.free()
+
+    if "link" in colls and n > 1:
+        # raw NVLink rates of the copy kernel between neighbours: the roofline of the P2P collectives
+        names = {0: "all ranks pull from rank+1", 1: "all ranks push to rank+1", 2: "rank 0 pulls from rank 1 (one direction busy)",
+                 3: "rank 0 pushes to rank 1 (one direction busy)", 4: "all ranks pull and push at once"}
+        for S in (64 << 20, 256 << 20):
+            for mode in range(5):
+                ms = ctypes.c_float()
+                if lib.b200mpi_link_probe(S, mode, 10, ctypes.byref(ms)):
+                    raise RuntimeError(L.last_error())
+                t = maxr(ms.value * 1e-3)
+                per_dir = (2 if mode == 4 else 1) * S / t / 1e9 if t > 0 else 0.0
+                emit({"coll": "link", "algo": names[mode], "mode": mode, "bytes": S, "t_us": t * 1e6, "gbs_per_direction": per_dir, "busbw_gbs": per_dir, "ok": True})
 
     if "latency" in colls and n > 1:
         # blocking-call latency of small Allreduce (what a Go caller sees per call): device-resident and
@@ -156,7 +174,7 @@ def main():
             if algo == "nvls" and not nvls:
                 continue
             lib.b200mpi_set_algo(L.COLL_ALLREDUCE, ALGOS[algo])
-            for S in (8, 64, 512, 4096, 32768):
+            for S in (8, 1024, 32768):
                 cnt = S // 4
                 for kind, sp, rp, mk in (("device", dsend.ptr, drecv.ptr, L.DEVICE), ("host", hin, hout, L.HOST)):
                     ts = []
@@ -178,11 +196,14 @@ def main():
 
     if "bcast" in colls and n > 1:
         buf = mpi.Alloc(maxc, np.float32)
-        for algo in ("oneshot", "twoshot", "nvls"):
-            if algo == "nvls" and not nvls:
+        for algo in ("oneshot", "twoshot", "nvls", "nvls_root"):
+            if algo.startswith("nvls") and not nvls:
                 continue
-            lib.b200mpi_set_algo(L.COLL_BCAST, ALGOS[algo])
+            lib.b200mpi_set_param(b"bcast_nvls2", 0 if algo == "nvls_root" else 1)
+            lib.b200mpi_set_algo(L.COLL_BCAST, ALGOS["nvls" if algo == "nvls_root" else algo])
             for S in sizes:
+                if algo == "oneshot" and S > (64 << 20):
+                    continue
                 cnt = S // 4
                 buf[:cnt].copy_from_host(np.full(cnt, 7.0 if rank == 0 else -1.0, dtype=np.float32)) if S <= (64 << 20) else None
                 it, wm = iters_for(S)
@@ -197,7 +218,9 @@ def main():
         per_max = min(args.max_bytes // n, 128 << 20)
         send = mpi.Alloc(per_max // 8, np.int64).copy_from_host(np.full(per_max // 8, rank + 1, dtype=np.int64))
         recv = mpi.Alloc(per_max // 8 * n, np.int64)
-        for algo in ("auto", "ring"):
+        for algo in ("oneshot", "ring", "nvls"):
+            if algo == "nvls" and not nvls:
+                continue
             lib.b200mpi_set_algo(L.COLL_ALLGATHER, ALGOS[algo])
             for S in [s for s in sizes if s <= per_max] + [1000000 * 8]:
                 if S > per_max:
@@ -208,7 +231,7 @@ def main():
                 got = recv[:cnt * n].to_host() if S * n <= (64 << 20) else None
                 ok = bool(all(np.all(got[r * cnt:(r + 1) * cnt] == r + 1) for r in range(n))) if got is not None else None
                 tot = S * n
-                emit({"coll": "allgather", "dtype": "i64", "algo": "push" if algo == "auto" else "ring", "bytes_per_rank": S, "bytes": tot, "t_us": t * 1e6,
+                emit({"coll": "allgather", "dtype": "i64", "algo": "push" if algo == "oneshot" else algo, "bytes_per_rank": S, "bytes": tot, "t_us": t * 1e6,
                       "algbw_gbs": tot / t / 1e9, "busbw_gbs": tot / t / 1e9 * (n - 1) / n, "ok": ok})
         lib.b200mpi_set_algo(L.COLL_ALLGATHER, 0)
         send.free()
