@@ -251,8 +251,19 @@ func (c *Cuda) Receive(data interface{}, source, tag int) error {
 	return gob.NewDecoder(bytes.NewReader(b)).Decode(data)
 }
 
+// lowerTyped is lower() for the collectives: only typed slices, Raw and *DeviceSlice qualify. A
+// gob-encoded temporary would receive the result instead of the caller's value (and its length
+// may differ from rank to rank), so anything else is an error rather than a silent no-op.
+func lowerTyped(what string, data interface{}) (unsafe.Pointer, int, C.int, C.int, error) {
+	switch data.(type) {
+	case *DeviceSlice, []float64, []float32, []int64, []byte, Raw:
+		return lower(data)
+	}
+	return nil, 0, 0, 0, fmt.Errorf("mpi: %s needs []float64, []float32, []int64, []byte, Raw or *DeviceSlice, got %T", what, data)
+}
+
 func (c *Cuda) Bcast(data interface{}, root int) error {
-	p, n, dt, kind, err := lower(data)
+	p, n, dt, kind, err := lowerTyped("Bcast", data)
 	if err != nil {
 		return err
 	}
@@ -263,11 +274,11 @@ func (c *Cuda) Bcast(data interface{}, root int) error {
 }
 
 func (c *Cuda) Allreduce(send, recv interface{}, op Op) error {
-	sp, sn, sdt, sk, err := lower(send)
+	sp, sn, sdt, sk, err := lowerTyped("Allreduce", send)
 	if err != nil {
 		return err
 	}
-	rp, rn, rdt, rk, err := lower(recv)
+	rp, rn, rdt, rk, err := lowerTyped("Allreduce", recv)
 	if err != nil {
 		return err
 	}
@@ -281,11 +292,11 @@ func (c *Cuda) Allreduce(send, recv interface{}, op Op) error {
 }
 
 func (c *Cuda) Allgather(send, recv interface{}) error {
-	sp, sn, sdt, sk, err := lower(send)
+	sp, sn, sdt, sk, err := lowerTyped("Allgather", send)
 	if err != nil {
 		return err
 	}
-	rp, rn, rdt, rk, err := lower(recv)
+	rp, rn, rdt, rk, err := lowerTyped("Allgather", recv)
 	if err != nil {
 		return err
 	}
@@ -294,6 +305,89 @@ func (c *Cuda) Allgather(send, recv interface{}) error {
 	}
 	if rc := C.b200mpi_allgather(sp, rp, C.size_t(sn), sdt, sk); rc != 0 {
 		return lastError(rc, 0)
+	}
+	return nil
+}
+
+// ReduceScatter: send holds Size() blocks of len(recv); rank j receives the reduction of block j.
+func (c *Cuda) ReduceScatter(send, recv interface{}, op Op) error {
+	sp, sn, sdt, sk, err := lowerTyped("ReduceScatter", send)
+	if err != nil {
+		return err
+	}
+	rp, rn, rdt, rk, err := lowerTyped("ReduceScatter", recv)
+	if err != nil {
+		return err
+	}
+	if sn != rn*c.Size() || sdt != rdt || sk != rk {
+		return errors.New("mpi: ReduceScatter send must hold Size()*len(recv) elements of the same type")
+	}
+	if rc := C.b200mpi_reduce_scatter(sp, rp, C.size_t(rn), sdt, C.int(op), sk); rc != 0 {
+		return lastError(rc, 0)
+	}
+	return nil
+}
+
+// Reduce: Allreduce whose result lands on root only (recv may be nil elsewhere).
+func (c *Cuda) Reduce(send, recv interface{}, op Op, root int) error {
+	sp, sn, sdt, sk, err := lowerTyped("Reduce", send)
+	if err != nil {
+		return err
+	}
+	var rp unsafe.Pointer
+	if recv != nil {
+		var rn int
+		var rdt, rk C.int
+		rp, rn, rdt, rk, err = lowerTyped("Reduce", recv)
+		if err != nil {
+			return err
+		}
+		if sn != rn || sdt != rdt || sk != rk {
+			return errors.New("mpi: Reduce send and recv must have the same type, length and memory kind")
+		}
+	}
+	if rc := C.b200mpi_reduce(sp, rp, C.size_t(sn), sdt, C.int(op), C.int(root), sk); rc != 0 {
+		return lastError(rc, 0)
+	}
+	return nil
+}
+
+// Alltoall: block j of send becomes block Rank() of rank j's recv.
+func (c *Cuda) Alltoall(send, recv interface{}) error {
+	sp, sn, sdt, sk, err := lowerTyped("Alltoall", send)
+	if err != nil {
+		return err
+	}
+	rp, rn, rdt, rk, err := lowerTyped("Alltoall", recv)
+	if err != nil {
+		return err
+	}
+	if sn != rn || sn%c.Size() != 0 || sdt != rdt || sk != rk {
+		return errors.New("mpi: Alltoall send and recv must both hold Size() equal blocks of the same type")
+	}
+	if rc := C.b200mpi_alltoall(sp, rp, C.size_t(sn/c.Size()), sdt, sk); rc != 0 {
+		return lastError(rc, 0)
+	}
+	return nil
+}
+
+// Isend is the Send of the design the reference sketches and comments out (mpi.go:132-143): it
+// returns once data may be modified again, without waiting for the receiver.
+func (c *Cuda) Isend(data interface{}, destination, tag int) error {
+	p, n, dt, kind, err := lower(data)
+	if err != nil {
+		return err
+	}
+	if rc := C.b200mpi_isend(p, C.size_t(n), dt, C.int(destination), C.int(tag), kind); rc != 0 {
+		return lastError(rc, tag)
+	}
+	return nil
+}
+
+// Wait blocks until destination confirmed the message sent with tag and frees the pair (mpi.go:146-152).
+func (c *Cuda) Wait(destination, tag int) error {
+	if rc := C.b200mpi_wait(C.int(destination), C.int(tag)); rc != 0 {
+		return lastError(rc, tag)
 	}
 	return nil
 }

@@ -23,6 +23,8 @@
 //	Allreduce  element-wise reduction over ranks, result on every rank
 //	Allgather  concatenation in rank order on every rank
 //	Barrier    rendezvous of all ranks
+//	ReduceScatter, Reduce, Alltoall   the usual MPI companions of the above
+//	Isend + Wait   the non-blocking Send design the reference sketches and comments out (mpi.go:132-152)
 //
 // They are served through the optional Collective interface, the upgrade the reference hints at
 // with its unused isAllReducer variable (mpi.go:69-71).
@@ -55,6 +57,15 @@ type Collective interface {
 	Allreduce(send, recv interface{}, op Op) error
 	Allgather(send, recv interface{}) error
 	Barrier() error
+}
+
+// Collective2 is the second optional upgrade: further collectives and the Isend/Wait pair.
+type Collective2 interface {
+	ReduceScatter(send, recv interface{}, op Op) error
+	Reduce(send, recv interface{}, op Op, root int) error
+	Alltoall(send, recv interface{}) error
+	Isend(data interface{}, destination, tag int) error
+	Wait(destination, tag int) error
 }
 
 // Raw marks a payload that is sent as bytes without any encoding.
@@ -163,4 +174,59 @@ func Barrier() error {
 		return err
 	}
 	return c.Barrier()
+}
+
+func collective2() (Collective2, error) {
+	if c, ok := current.(Collective2); ok {
+		return c, nil
+	}
+	return nil, fmt.Errorf("mpi: registered implementation %T has no ReduceScatter/Reduce/Alltoall/Isend", current)
+}
+
+// ReduceScatter reduces block j of every rank's send (Size() blocks of len(recv)) into rank j's recv.
+func ReduceScatter(send, recv interface{}, op Op) error {
+	c, err := collective2()
+	if err != nil {
+		return err
+	}
+	return c.ReduceScatter(send, recv, op)
+}
+
+// Reduce is Allreduce with the result on root only; recv may be nil on the other ranks.
+func Reduce(send, recv interface{}, op Op, root int) error {
+	c, err := collective2()
+	if err != nil {
+		return err
+	}
+	return c.Reduce(send, recv, op, root)
+}
+
+// Alltoall sends block j of send to rank j, where it becomes block Rank() of recv.
+func Alltoall(send, recv interface{}) error {
+	c, err := collective2()
+	if err != nil {
+		return err
+	}
+	return c.Alltoall(send, recv)
+}
+
+// Isend transmits data to destination and returns once data may be modified again, without
+// waiting for the receiver (the Send of the reference's commented-out design, mpi.go:132-143).
+// The {destination, tag} pair stays in use until Wait.
+func Isend(data interface{}, destination, tag int) error {
+	c, err := collective2()
+	if err != nil {
+		return err
+	}
+	return c.Isend(data, destination, tag)
+}
+
+// Wait blocks until destination confirmed the message sent with tag, and frees the pair for
+// re-use (mpi.go:146-152).
+func Wait(destination, tag int) error {
+	c, err := collective2()
+	if err != nil {
+		return err
+	}
+	return c.Wait(destination, tag)
 }

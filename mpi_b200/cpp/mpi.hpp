@@ -13,7 +13,8 @@
 //   mpi.Receive(&data, src, tag)               mpi::Error mpi::Receive(T* data, int src, int tag)   (resizes *data like gob)
 //   mpi.Register(impl)                         void mpi::Register(Interface*)  (second call throws = panics, mpi.go:61-67)
 //   flag.Parse() + mpi.Flag*                   mpi::ParseFlags(argc, argv) + mpi::Flag*
-//   new: Recv, Bcast, Allreduce, Allgather, Barrier; mpi::DeviceSlice<T> for heap-resident buffers
+//   new: Recv, Bcast, Allreduce, Allgather, Barrier, ReduceScatter, Reduce, Alltoall, Isend/Wait;
+//        mpi::DeviceSlice<T> for heap-resident buffers
 // `data` may be std::vector<double|float|int64_t|uint8_t>, std::string (sent as bytes, the
 // "anything else is gob-encoded" path), or DeviceSlice<T>.
 #pragma once
@@ -170,6 +171,12 @@ struct Interface {
   virtual Error Allreduce(Buffer, Buffer, Op) { Error e; e.code = B200MPI_ERR_UNSUPPORTED; e.msg = "registered implementation has no Allreduce"; return e; }
   virtual Error Allgather(Buffer, Buffer) { Error e; e.code = B200MPI_ERR_UNSUPPORTED; e.msg = "registered implementation has no Allgather"; return e; }
   virtual Error Barrier() { Error e; e.code = B200MPI_ERR_UNSUPPORTED; e.msg = "registered implementation has no Barrier"; return e; }
+  virtual Error ReduceScatter(Buffer, Buffer, Op) { Error e; e.code = B200MPI_ERR_UNSUPPORTED; e.msg = "registered implementation has no ReduceScatter"; return e; }
+  virtual Error Reduce(Buffer, Buffer, Op, int) { Error e; e.code = B200MPI_ERR_UNSUPPORTED; e.msg = "registered implementation has no Reduce"; return e; }
+  virtual Error Alltoall(Buffer, Buffer) { Error e; e.code = B200MPI_ERR_UNSUPPORTED; e.msg = "registered implementation has no Alltoall"; return e; }
+  // the Send/Wait pair the reference sketches and comments out (mpi.go:132-152)
+  virtual Error Isend(Buffer, int, int) { Error e; e.code = B200MPI_ERR_UNSUPPORTED; e.msg = "registered implementation has no Isend"; return e; }
+  virtual Error Wait(int, int) { Error e; e.code = B200MPI_ERR_UNSUPPORTED; e.msg = "registered implementation has no Wait"; return e; }
 };
 
 // The B200 implementation; plays the role of `Network` (network.go:25-39): fields win over flags.
@@ -198,6 +205,11 @@ struct Cuda : Interface {
   Error Allreduce(Buffer s, Buffer r, Op op) override { return make_error(b200mpi_allreduce(s.ptr, r.ptr, s.count, s.dtype, op, s.memkind)); }
   Error Allgather(Buffer s, Buffer r) override { return make_error(b200mpi_allgather(s.ptr, r.ptr, s.count, s.dtype, s.memkind)); }
   Error Barrier() override { return make_error(b200mpi_barrier()); }
+  Error ReduceScatter(Buffer s, Buffer r, Op op) override { return make_error(b200mpi_reduce_scatter(s.ptr, r.ptr, r.count, s.dtype, op, s.memkind)); }
+  Error Reduce(Buffer s, Buffer r, Op op, int root) override { return make_error(b200mpi_reduce(s.ptr, r.ptr, s.count, s.dtype, op, root, s.memkind)); }
+  Error Alltoall(Buffer s, Buffer r) override { return make_error(b200mpi_alltoall(s.ptr, r.ptr, s.count / (size_t)(Size() > 0 ? Size() : 1), s.dtype, s.memkind)); }
+  Error Isend(Buffer d, int destination, int tag) override { return make_error(b200mpi_isend(d.ptr, d.count, d.dtype, destination, tag, d.memkind)); }
+  Error Wait(int destination, int tag) override { return make_error(b200mpi_wait(destination, tag)); }
 };
 
 inline Interface*& mpier() { // var mpier Interface = &Network{}  (mpi.go:56)
@@ -260,5 +272,22 @@ template <typename T> inline Error Allgather(const std::vector<T>& send, std::ve
 }
 template <typename T> inline Error Allgather(const DeviceSlice<T>& send, DeviceSlice<T>* recv) { return mpier()->Allgather(lower(send), lower(*recv)); }
 inline Error Barrier() { return mpier()->Barrier(); }
+
+// send holds Size() blocks; rank j receives the reduction of block j (recv is resized to one block)
+template <typename T> inline Error ReduceScatter(const std::vector<T>& send, std::vector<T>* recv, Op op = SUM) {
+  recv->resize(send.size() / (size_t)Size());
+  return mpier()->ReduceScatter(lower(send), lower(*recv), op);
+}
+template <typename T> inline Error ReduceScatter(const DeviceSlice<T>& send, DeviceSlice<T>* recv, Op op = SUM) { return mpier()->ReduceScatter(lower(send), lower(*recv), op); }
+template <typename T> inline Error Reduce(const std::vector<T>& send, std::vector<T>* recv, Op op, int root) {
+  if (Rank() == root) recv->resize(send.size());
+  return mpier()->Reduce(lower(send), lower(*recv), op, root);
+}
+template <typename T> inline Error Alltoall(const std::vector<T>& send, std::vector<T>* recv) {
+  recv->resize(send.size());
+  return mpier()->Alltoall(lower(send), lower(*recv));
+}
+template <typename D> inline Error Isend(const D& data, int destination, int tag) { return mpier()->Isend(lower(data), destination, tag); }
+inline Error Wait(int destination, int tag) { return mpier()->Wait(destination, tag); }
 
 } // namespace mpi

@@ -248,8 +248,8 @@ struct Ctx {
   std::atomic<int64_t> launches{0};
   static constexpr int kBounceSlots = 4;
   char* bounce = nullptr;      // pinned ring for pageable host slices: [in kBounceSlots][out kBounceSlots] x bounce_chunk
-  size_t bounce_chunk = 0, bounce_chunk_bytes = 8u << 20;
-  int host_threads = 4;        // helper threads copying between pageable memory and the bounce ring
+  size_t bounce_chunk = 0, bounce_chunk_bytes = 4u << 20;
+  int host_threads = 8;        // helper threads copying between pageable memory and the bounce ring
   CopyPool pool;
   int gpu_numa_node = -1;      // NUMA node of the bound GPU (-1 unknown): host buffers and helper threads go there
   size_t oneshot_max_bytes = 256u << 10;
@@ -741,7 +741,7 @@ static int pick_allreduce(size_t bytes, int dtype, int op, bool chunk = false) {
   if (forced == B200MPI_ALGO_TWOSHOT_SMEM && !pow2) forced = B200MPI_ALGO_TWOSHOT;
   if (forced == B200MPI_ALGO_NVLS && !can_nvls) forced = 0;
   if (forced == B200MPI_ALGO_HYBRID && !(can_nvls && pow2 && g->hybrid_p2p_permille > 0)) forced = can_nvls ? B200MPI_ALGO_NVLS : 0;
-  if (forced == B200MPI_ALGO_LL && (bytes > kLLCells * 8 || chunk)) forced = chunk ? B200MPI_ALGO_ONESHOT : 0;
+  if (forced == B200MPI_ALGO_LL && (bytes > ll_cells(g->ctrl.n) * 8 || chunk)) forced = chunk ? B200MPI_ALGO_ONESHOT : 0;
   if (forced == B200MPI_ALGO_ONESHOT && es && oneshot_plan(bytes / es, es).rounds > kMaxMids) forced = B200MPI_ALGO_TWOSHOT;
   if (forced) return forced;
   if (g->ll_max_bytes && bytes <= g->ll_max_bytes && !chunk) return B200MPI_ALGO_LL;
@@ -946,7 +946,7 @@ static int launch_ll_t(const void* send, void* recv, size_t count, uint32_t* don
   Comm c = g->comm;
   const uint32_t seq = ++g->ll_seq;
   const size_t ncell = (count * sizeof(T) + 7) / 8;
-  const int blocks = (int)std::max<size_t>(1, std::min<size_t>((ncell + 511) / 512, 32));
+  const int blocks = (int)std::max<size_t>(1, std::min<size_t>((ncell + 511) / 512, ncell > 32768 ? 64 : 32));
   allreduce_ll_kernel<T, Op><<<blocks, 256, 0, s>>>(c, (const T*)send, (T*)recv, count, seq, done_host);
   return launch_check("allreduce_ll_kernel");
 }
@@ -972,7 +972,7 @@ static int launch_ll(int dtype, int op, const void* send, void* recv, size_t cou
 // H2D / D2H copies, no stream synchronisation), memcpy out.
 static int allreduce_ll_host(const void* send, void* recv, size_t count, int dtype, int op) {
   const size_t bytes = count * esize(dtype);
-  const size_t half = kLLCells * 8;
+  const size_t half = kLLRegionCells / 4 * 8; // the largest message of any world size (n = 2)
   if (!g->ll_host) {
     CUDA_OK(cudaHostAlloc((void**)&g->ll_host, 2 * half + 64, cudaHostAllocMapped));
     CUDA_OK(cudaHostGetDevicePointer((void**)&g->ll_dev, g->ll_host, 0));
@@ -1581,12 +1581,12 @@ static void apply_defaults() {
   const int n = g->ctrl.n;
   const bool nvls = g->heap.mc_base != 0;
   g->ll_max_bytes = 0;
-  if (!g->shared_device) g->ll_max_bytes = n >= 8 ? (32u << 10) : (64u << 10);
+  if (!g->shared_device) g->ll_max_bytes = n >= 8 ? (32u << 10) : n >= 3 ? (64u << 10) : (256u << 10); // 2 GPUs: LL 12.3 us vs 14.5 (nvls) at 256 KiB
   g->bcast_nvls_min = 4u << 20;
   g->allgather_nvls_min = 1u << 20;
   g->hybrid_p2p_permille = 0;
   (void)nvls;
-  if (const char* w = getenv("B200MPI_LL_MAX")) g->ll_max_bytes = std::min<size_t>(strtoull(w, nullptr, 0), kLLCells * 8);
+  if (const char* w = getenv("B200MPI_LL_MAX")) g->ll_max_bytes = std::min<size_t>(strtoull(w, nullptr, 0), ll_cells(g->ctrl.n) * 8);
   if (const char* w = getenv("B200MPI_HYBRID_PERMILLE")) g->hybrid_p2p_permille = std::max(0, std::min(900, atoi(w)));
 }
 
@@ -1947,7 +1947,7 @@ int b200mpi_set_param(const char* name, int64_t value) {
   else if (k == "nvls_unroll") g->nvls_unroll = (int)value;
   else if (k == "nvls_min_ranks") g->nvls_min_ranks = (int)value;
   else if (k == "copy_variant") g->copy_variant = (int)value;
-  else if (k == "ll_max_bytes") g->ll_max_bytes = (size_t)std::min<int64_t>(std::max<int64_t>(value, 0), (int64_t)(kLLCells * 8));
+  else if (k == "ll_max_bytes") g->ll_max_bytes = (size_t)std::min<int64_t>(std::max<int64_t>(value, 0), (int64_t)(ll_cells(g->ctrl.n) * 8));
   else if (k == "nvls_max_blocks") g->nvls_max_blocks = (int)std::max<int64_t>(1, value);
   else if (k == "oneshot_max_bytes") g->oneshot_max_bytes = (size_t)value;
   else if (k == "pipe_min_bytes") g->pipe_min_bytes = (size_t)value;

@@ -30,8 +30,10 @@ constexpr int kMaxBlocks = 592;            // 148 SMs x 4
 constexpr size_t kCtrlBytes = 16u << 20;   // control region at the start of every heap (== kHeapReserved, heap.h)
 constexpr size_t kRingFlagsOff = 512u << 10;
 constexpr size_t kLLStateOff = 768u << 10;   // LL bookkeeping words (device-resident sequence number, CTA counter)
-constexpr size_t kLLOff = 1u << 20;          // LL cells: [parity 2][src rank 8][kLLCells] x 16 B = 8 MiB
-constexpr size_t kLLCells = 32768;           // 8 payload bytes per cell -> 256 KiB per call
+constexpr size_t kLLOff = 1u << 20;          // LL cells: [parity 2][src rank n][ll_cells(n)] x 16 B, 8 MiB in all
+constexpr size_t kLLRegionCells = 2 * 8 * 32768;
+// cells per lane: 8 payload bytes each -> 256 KiB per call at n = 8, 512 KiB at n = 4, 1 MiB at n = 2
+__host__ __device__ constexpr size_t ll_cells(int n) { return kLLRegionCells / (2 * (size_t)(n < 1 ? 1 : n)); }
 constexpr int kThreads = 512;
 // Every collective launch consumes exactly kEpochStride flag values, whatever the algorithm:
 // start barrier = epoch, mid barriers = epoch+1 .. epoch+kEpochStride-2, end barrier =
@@ -40,18 +42,18 @@ constexpr int kThreads = 512;
 constexpr uint32_t kEpochStride = 4096;
 constexpr uint32_t kMaxMids = kEpochStride - 2;
 
-struct __align__(32) Slot {
+// One slot per (CTA, source rank).  The start barrier needs no release fence: the three cells are
+// plain 16-byte stores that carry their own flag next to every 8 payload bytes (the LL idea: only
+// 8-byte store atomicity is assumed), so a peer's {send offset, recv offset, signature} are valid
+// as soon as all six flag words equal this call's epoch -- one NVLink one-way latency instead of a
+// round trip (release = wait for the acks of the payload stores) plus a one-way.  `flag` is the
+// release/acquire word of the mid and end barriers, where the body's stores must have landed.
+struct __align__(64) Slot {
+  uint4 cell[3];    // {lo32, epoch, hi32, epoch} of: a = writer's send offset, b = recv offset, c = signature
   uint32_t flag;
-  uint32_t pad;
-  uint64_t a; // send offset of the writer for this call
-  uint64_t b; // recv offset
-  uint64_t c;
+  uint32_t pad[3];
 };
-static_assert(sizeof(Slot) == 32, "slot size");
-static_assert(sizeof(Slot) * kMaxBlocks * kMaxRanks <= kRingFlagsOff, "control region layout");
-static_assert(kRingFlagsOff + 4 * kMaxBlocks <= kLLStateOff && kLLStateOff + 4096 <= kLLOff, "control region layout");
-static_assert(kLLOff + 2 * kMaxRanks * kLLCells * 16 <= kCtrlBytes, "control region layout");
-
+static_assert(sizeof(Slot) == 64, "slot size");
 struct Comm {
   char* base[kMaxRanks];     // heap of rank r as mapped in this process
   char* mc;                  // multicast (NVLS) mapping of all heaps, or nullptr
@@ -122,6 +124,38 @@ __device__ __forceinline__ Slot* slot_of(const Comm& c, int owner, int block, in
 // without a partner learns it there instead of waiting for a flag that never comes.  (While the
 // grids match the row cannot be overwritten early: a peer's next kernel starts only after its
 // current one has finished, which needs this CTA to have passed sync_end.)
+__device__ __forceinline__ void st_cell16(uint4* p, uint4 v) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_cell16(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+// Spin until the three cells of `s` carry `epoch`; values out through a/b/sig.  false on watchdog expiry.
+__device__ __forceinline__ bool wait_cells(const Slot* s, uint32_t epoch, const Comm& c, uint64_t& a, uint64_t& b, uint64_t& sig) {
+  unsigned long long t0 = 0;
+  uint32_t it = 0;
+  for (;;) {
+    const uint4 x = ld_cell16(&s->cell[0]), y = ld_cell16(&s->cell[1]), z = ld_cell16(&s->cell[2]);
+    if (x.y == epoch && x.w == epoch && y.y == epoch && y.w == epoch && z.y == epoch && z.w == epoch) {
+      a = ((uint64_t)x.z << 32) | x.x;
+      b = ((uint64_t)y.z << 32) | y.x;
+      sig = ((uint64_t)z.z << 32) | z.x;
+      return true;
+    }
+    if ((++it & 0xfffu) == 0) {
+      const unsigned long long now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (c.timeout_ns && now - t0 > c.timeout_ns) {
+        *(volatile uint32_t*)c.status = 1u;
+        __threadfence_system();
+        return false;
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ bool sync_start(const Comm& c, uint64_t a, uint64_t b, uint64_t* s_a,
                                            uint64_t* s_b) {
   __shared__ int s_bad;
@@ -130,23 +164,21 @@ __device__ __forceinline__ bool sync_start(const Comm& c, uint64_t a, uint64_t b
   __syncthreads();
   if (t < c.n) {
     Slot* theirs = slot_of(c, t, blockIdx.x, c.rank);
-    st_relaxed_sys_u64(&theirs->a, a);
-    st_relaxed_sys_u64(&theirs->b, b);
-    st_relaxed_sys_u64(&theirs->c, c.sig);
-    st_release_sys(&theirs->flag, c.epoch);
+    st_cell16(&theirs->cell[0], make_uint4((uint32_t)a, c.epoch, (uint32_t)(a >> 32), c.epoch));
+    st_cell16(&theirs->cell[1], make_uint4((uint32_t)b, c.epoch, (uint32_t)(b >> 32), c.epoch));
+    st_cell16(&theirs->cell[2], make_uint4((uint32_t)c.sig, c.epoch, (uint32_t)(c.sig >> 32), c.epoch));
     bool ok = true;
+    uint64_t pa, pb, psig;
     if (blockIdx.x != 0) {
-      Slot* lead = slot_of(c, c.rank, 0, t);
-      if (!wait_flag(&lead->flag, c.epoch, c)) { s_bad = 2; ok = false; }
-      else if (ld_relaxed_sys_u64(&lead->c) != c.sig) { s_bad = 1; ok = false; }
+      if (!wait_cells(slot_of(c, c.rank, 0, t), c.epoch, c, pa, pb, psig)) { s_bad = 2; ok = false; }
+      else if (psig != c.sig) { s_bad = 1; ok = false; }
     }
     if (ok) {
-      Slot* mine = slot_of(c, c.rank, blockIdx.x, t);
-      if (!wait_flag(&mine->flag, c.epoch, c)) s_bad = 2;
+      if (!wait_cells(slot_of(c, c.rank, blockIdx.x, t), c.epoch, c, pa, pb, psig)) s_bad = 2;
       else {
-        s_a[t] = ld_relaxed_sys_u64(&mine->a);
-        s_b[t] = ld_relaxed_sys_u64(&mine->b);
-        if (ld_relaxed_sys_u64(&mine->c) != c.sig) s_bad = 1;
+        s_a[t] = pa;
+        s_b[t] = pb;
+        if (psig != c.sig) s_bad = 1;
       }
     }
   }
@@ -1399,7 +1431,7 @@ copy_bytes_kernel(unsigned char* __restrict__ dst, const unsigned char* __restri
 // and recv may be any local device pointers.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint4* ll_lane(const Comm& c, int owner, uint32_t parity, int src) {
-  return reinterpret_cast<uint4*>(c.base[owner] + kLLOff) + ((size_t)parity * kMaxRanks + src) * kLLCells;
+  return reinterpret_cast<uint4*>(c.base[owner] + kLLOff) + ((size_t)parity * c.n + src) * ll_cells(c.n);
 }
 __device__ __forceinline__ void st_cell(uint4* p, uint4 v) {
   asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
