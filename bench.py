@@ -332,13 +332,35 @@ def main():
         scale = np.sum([np.abs(x.astype(np.float64)) for x in ins], axis=0)
         return bool(np.all(np.abs(got.astype(np.float64) - want.astype(np.float64)) <= 1e-6 * scale + 1e-300))
 
+    def ring_expect(ins, dt, cnt, lo, m):
+        """allreduce_ring_kernel's order for elements [lo, lo+m) of a cnt-element message: chunk c (of
+        ceil(groups/n) 16-byte groups) is summed cyclically from rank c; the count % EPV tail in rank order."""
+        epv = 16 // np.dtype(dt).itemsize
+        groups = cnt // epv
+        per = -(-groups // n) if groups else 0
+        want = np.empty(m, dtype=dt)
+        e = lo
+        while e < lo + m:
+            if e < groups * epv and per > 0:
+                c = (e // epv) // per
+                hi = min(lo + m, min((c + 1) * per, groups) * epv)
+                rot = [ins[(c + k) % n][e - lo:hi - lo] for k in range(n)]
+            else:
+                hi = lo + m
+                rot = [x[e - lo:hi - lo] for x in ins]
+            want[e - lo:hi - lo] = O.allreduce(rot, order=O.ORDER_RANK)
+            e = hi
+        return want
+
     def check_allreduce_blocks(dev, dt, cnt, seed, exact_order=None):
         ok = True
         for lo in range(0, cnt, BLOCK):
             m = min(BLOCK, cnt - lo)
             ins = [O.fill_at(dt, seed + r, lo, m) for r in range(n)]
             got = dev[lo:lo + m].to_host()
-            if exact_order is not None:
+            if exact_order == O.ORDER_RING:  # chunk boundaries are global: restate them per block
+                ok = ok and bool(np.array_equal(got, ring_expect(ins, dt, cnt, lo, m)))
+            elif exact_order is not None:
                 ok = ok and bool(np.array_equal(got, O.allreduce(ins, order=exact_order)))
             else:
                 ok = ok and close(got, O.allreduce(ins, order=O.ORDER_F64), ins)
@@ -458,17 +480,24 @@ def main():
         if n % 2 == 0:
             msg = O.fill(np.float64, SEED + 700 + (rank & ~1), pc)
             for kind in ("device", "host"):
+                # the same two allocations on every rank: the heaps stay laid out identically
+                b1 = mpi.Alloc(pc, np.float64) if kind == "device" else np.zeros(pc)
+                b2 = mpi.Alloc(pc, np.float64) if kind == "device" else np.zeros(pc)
                 if rank % 2 == 0:
-                    src = mpi.Alloc(pc, np.float64).copy_from_host(msg) if kind == "device" else np.array(msg)
-                    back = mpi.Alloc(pc, np.float64) if kind == "device" else np.zeros(pc)
-                    mpi.Send(src, rank + 1, 3)
-                    back = mpi.Receive(back, rank + 1, 3)
+                    if kind == "device":
+                        b1.copy_from_host(msg)
+                    else:
+                        b1[:] = msg
+                    mpi.Send(b1, rank + 1, 3)
+                    back = mpi.Receive(b2, rank + 1, 3)
                     got = back.to_host() if kind == "device" else back
                     ok = ok and bool(np.array_equal(got, msg))
                 else:
-                    tmp = mpi.Alloc(pc, np.float64) if kind == "device" else np.zeros(pc)
-                    tmp = mpi.Receive(tmp, rank - 1, 3)
+                    tmp = mpi.Receive(b1, rank - 1, 3)
                     mpi.Send(tmp, rank - 1, 3)
+                if kind == "device":
+                    b1.free()
+                    b2.free()
         parity["bounce_f64_1MiB"] = ok
         # every rank must agree that every check passed on every rank
         for k in list(parity):
@@ -557,6 +586,17 @@ def main():
         parity["e2e_pageable_result"] = close(pr[lo:], O.allreduce(ins, order=O.ORDER_F64), ins)
         e2e_pageable = {"value": S / t_pg / 1e9 * bus, "unit": "GB/s", "ms_per_step": t_pg * 1e3, "steps": k_e2e,
                         "host_memory": "pageable numpy arrays through a pinned bounce ring", "vs_pinned": t_pg / t_e2e}
+        # opt-in mode for callers whose buffers stay mapped: pin them in place once (cudaHostRegister, cached)
+        lib.b200mpi_set_param(b"host_register", 1)
+        t_first0 = time.perf_counter()
+        if lib.b200mpi_allreduce(ps.ctypes.data, pr.ctypes.data, count, L.F32, L.SUM, L.HOST):
+            raise RuntimeError(L.last_error())
+        t_first = max_over_ranks(time.perf_counter() - t_first0)
+        t_reg = timed_host(ps.ctypes.data, pr.ctypes.data)
+        lib.b200mpi_set_param(b"host_register", 0)
+        parity["e2e_pageable_result"] = parity["e2e_pageable_result"] and close(pr[lo:], O.allreduce(ins, order=O.ORDER_F64), ins)
+        e2e_pageable["registered"] = {"value": S / t_reg / 1e9 * bus, "unit": "GB/s", "ms_per_step": t_reg * 1e3, "vs_pinned": t_reg / t_e2e, "first_call_ms": t_first * 1e3,
+                                      "note": "opt-in B200MPI_HOST_REGISTER=1: the caller's arrays are pinned in place on first use (cached by address range), then DMA'd directly"}
         for k in ("e2e_host_result", "e2e_pageable_result"):
             parity[k] = all_ranks(parity[k]) if n > 1 else bool(parity[k])
         parity_ok = all(parity.values())

@@ -251,6 +251,12 @@ struct Ctx {
   size_t bounce_chunk = 0, bounce_chunk_bytes = 4u << 20;
   int host_threads = 8;        // helper threads copying between pageable memory and the bounce ring
   CopyPool pool;
+  // Opt-in (B200MPI_HOST_REGISTER=1 / "host_register"): pin the caller's pageable buffers in place
+  // (cudaHostRegister, cached by address range) instead of bouncing them.  Only for callers whose
+  // buffers stay mapped for the life of the cache (a freed and re-mapped range would alias stale
+  // pinned pages); off by default.
+  int host_register = 0;
+  std::vector<std::pair<uintptr_t, size_t>> registered; // LRU, most recent last
   int gpu_numa_node = -1;      // NUMA node of the bound GPU (-1 unknown): host buffers and helper threads go there
   size_t oneshot_max_bytes = 256u << 10;
   int hybrid_p2p_permille = 0; // Allreduce HYBRID: share of the message that goes the P2P way, in 1/1000
@@ -259,7 +265,7 @@ struct Ctx {
   size_t bcast_nvls_min = 0, allgather_nvls_min = 0; // AUTO thresholds (bytes), set at init from n
   int twoshot_unroll = 1; // 0: 1/2/4 vectors per thread for n = 8/4/2, 1: 2/4/8
   int nvls_unroll = 2;      // 8 GPUs, 256 MiB: unroll 2 x 64 CTAs 810 GB/s, 4 x 148 CTAs 780 (profiles/r01/sweep_n8_nvls_blocks_unroll_v2.jsonl)
-  int nvls_max_blocks = 64; // fewer requests in flight suit the switch reduction better
+  int nvls_max_blocks = 48; // fewer requests in flight suit the switch reduction better (r02: 48 CTAs 822/845 GB/s at 256 MiB/1 GiB, 64 CTAs 817/840)
   size_t ll_max_bytes = 0; // AUTO uses the barrier-free LL allreduce for messages up to this size (<= 256 KiB)
   uint32_t ll_seq = 0;
   // pinned, device-mapped bounce buffers: a small host-slice Allreduce is a memcpy + ONE kernel that
@@ -946,7 +952,7 @@ static int launch_ll_t(const void* send, void* recv, size_t count, uint32_t* don
   Comm c = g->comm;
   const uint32_t seq = ++g->ll_seq;
   const size_t ncell = (count * sizeof(T) + 7) / 8;
-  const int blocks = (int)std::max<size_t>(1, std::min<size_t>((ncell + 511) / 512, ncell > 32768 ? 64 : 32));
+  const int blocks = (int)std::max<size_t>(1, std::min<size_t>((ncell + 255) / 256, 128)); // one cell per thread up to 256 KiB
   allreduce_ll_kernel<T, Op><<<blocks, 256, 0, s>>>(c, (const T*)send, (T*)recv, count, seq, done_host);
   return launch_check("allreduce_ll_kernel");
 }
@@ -1015,6 +1021,29 @@ static bool is_pinned(const void* p) {
   return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
 }
 
+static bool ensure_registered(const void* p, size_t bytes) {
+  if (!p || bytes == 0) return true;
+  const uintptr_t page = 4096, lo = (uintptr_t)p & ~(page - 1), hi = ((uintptr_t)p + bytes + page - 1) & ~(page - 1);
+  for (size_t i = 0; i < g->registered.size(); ++i) {
+    auto e = g->registered[i];
+    if (lo >= e.first && hi <= e.first + e.second) {
+      g->registered.erase(g->registered.begin() + i);
+      g->registered.push_back(e);
+      return true;
+    }
+  }
+  // drop entries the new range overlaps (the caller re-used part of an old buffer) and the oldest beyond 16
+  for (size_t i = 0; i < g->registered.size();) {
+    auto e = g->registered[i];
+    if (lo < e.first + e.second && e.first < hi) { cudaHostUnregister((void*)e.first); g->registered.erase(g->registered.begin() + i); }
+    else ++i;
+  }
+  while (g->registered.size() >= 16) { cudaHostUnregister((void*)g->registered.front().first); g->registered.erase(g->registered.begin()); }
+  if (cudaHostRegister((void*)lo, hi - lo, cudaHostRegisterDefault) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+  g->registered.push_back({lo, hi - lo});
+  return true;
+}
+
 struct PipeSpec {
   int coll;          // B200MPI_COLL_ALLREDUCE / _BCAST / _ALLGATHER
   int dtype, op, root;
@@ -1040,7 +1069,10 @@ static int host_pipeline(const PipeSpec& sp) {
   const int n = g->ctrl.n, R = Ctx::kBounceSlots;
   const bool ag = sp.coll == B200MPI_COLL_ALLGATHER;
   const size_t rows = ag ? (size_t)n : 1;
-  const bool bounce = !(is_pinned(sp.in) && is_pinned(sp.out)) && g->host_threads > 0;
+  bool pinned = is_pinned(sp.in) && is_pinned(sp.out);
+  if (!pinned && g->host_register)
+    pinned = (is_pinned(sp.in) || ensure_registered(sp.in, sp.in ? B : 0)) && (is_pinned(sp.out) || ensure_registered(sp.out, sp.out ? B * rows : 0));
+  const bool bounce = !pinned && g->host_threads > 0;
   size_t chunk_bytes = g->pipe_chunk_bytes;
   if (bounce) chunk_bytes = std::min(chunk_bytes, g->bounce_chunk_bytes);
   size_t chunk_elems = std::max<size_t>(chunk_bytes / rows / es, 4096) / 4096 * 4096;
@@ -1582,8 +1614,12 @@ static void apply_defaults() {
   const bool nvls = g->heap.mc_base != 0;
   g->ll_max_bytes = 0;
   if (!g->shared_device) g->ll_max_bytes = n >= 8 ? (32u << 10) : n >= 3 ? (64u << 10) : (256u << 10); // 2 GPUs: LL 12.3 us vs 14.5 (nvls) at 256 KiB
-  g->bcast_nvls_min = 4u << 20;
-  g->allgather_nvls_min = 1u << 20;
+  // Measured on 8 B200s (profiles/r02/sweep_n8_bcag_v1.jsonl, sweep_n8_hybrid_v1.jsonl): multicast
+  // delivery tops out near 480-510 GB/s of ingress per GPU, below what plain P2P stores reach
+  // (620-650), so above a few MiB Bcast and Allgather stay on the P2P kernels; mixing P2P traffic
+  // into the NVLS allreduce only slows it (817 -> 793 GB/s at 10 %), so the hybrid stays off.
+  g->bcast_nvls_min = SIZE_MAX;
+  g->allgather_nvls_min = SIZE_MAX;
   g->hybrid_p2p_permille = 0;
   (void)nvls;
   if (const char* w = getenv("B200MPI_LL_MAX")) g->ll_max_bytes = std::min<size_t>(strtoull(w, nullptr, 0), ll_cells(g->ctrl.n) * 8);
@@ -1637,6 +1673,7 @@ int b200mpi_init(const char* addr, const char* alladdr_csv, const char* password
   if (!g->drv.load(err)) return bail(B200MPI_ERR_CUDA, err);
   if (!(getenv("B200MPI_NUMA") && atoi(getenv("B200MPI_NUMA")) == 0)) g->gpu_numa_node = numa_node_of_gpu(g->dev);
   if (const char* w = getenv("B200MPI_HOST_THREADS")) g->host_threads = std::max(0, atoi(w));
+  if (const char* w = getenv("B200MPI_HOST_REGISTER")) g->host_register = atoi(w) != 0;
 
   // who sits where: ranks sharing a device (functional-test mode) rule out NVLS
   struct Hello { unsigned char uuid[16]; int32_t dev; int32_t mc; } mine = {}, all[B200MPI_MAX_RANKS];
@@ -1724,6 +1761,7 @@ int b200mpi_finalize(void) {
     if (g->ll_host) cudaFreeHost(g->ll_host);
     if (g->pool.running()) g->pool.shutdown();
     if (g->bounce) cudaFreeHost(g->bounce);
+    for (auto& e : g->registered) cudaHostUnregister((void*)e.first);
     if (g->box) munmap(g->box, sizeof(Mailbox));
     {
       std::lock_guard<std::mutex> l(g_pending_mu);
@@ -1961,6 +1999,7 @@ int b200mpi_set_param(const char* name, int64_t value) {
   else if (k == "bcast_nvls2") g->bcast_nvls2 = value ? 1 : 0;
   else if (k == "bcast_nvls_min") g->bcast_nvls_min = (size_t)std::max<int64_t>(value, 0);
   else if (k == "allgather_nvls_min") g->allgather_nvls_min = (size_t)std::max<int64_t>(value, 0);
+  else if (k == "host_register") g->host_register = value ? 1 : 0;
   else if (k == "bounce_chunk_bytes") g->bounce_chunk_bytes = (size_t)std::max<int64_t>(value, 65536);
   else if (k == "host_threads") { if (g->pool.running()) return fail(B200MPI_ERR_ARG, "set_param: host_threads must be set before the first pageable host-slice call"); g->host_threads = (int)std::max<int64_t>(value, 0); }
   else return fail(B200MPI_ERR_ARG, "set_param: unknown parameter '" + k + "'");
@@ -1981,6 +2020,7 @@ int b200mpi_get_param(const char* name, int64_t* value) {
   else if (k == "pipe_chunk_bytes") *value = (int64_t)g->pipe_chunk_bytes;
   else if (k == "bounce_chunk_bytes") *value = (int64_t)g->bounce_chunk_bytes;
   else if (k == "host_threads") *value = g->host_threads;
+  else if (k == "host_register") *value = g->host_register;
   else if (k == "own_block_bytes") *value = (int64_t)g->own_block_bytes;
   else if (k == "stage_chunk") *value = (int64_t)g->stage_chunk;
   else if (k == "watchdog_ms") *value = g->watchdog_ns / 1000000ll;

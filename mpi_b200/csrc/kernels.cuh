@@ -1246,10 +1246,10 @@ bcast_nvls_kernel(Comm c, uint64_t buf_off, size_t bytes, int root) {
         }
       }
     }
-  } else if (c.rank != root) { // asymmetric buffers: pull bytes from root
-    const unsigned char* src = reinterpret_cast<const unsigned char*>(c.base[root] + s_a[root]);
-    unsigned char* dst = reinterpret_cast<unsigned char*>(c.base[c.rank] + buf_off);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < bytes; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+  } else if ((bytes & 15) == 0 && all_aligned_to(s_a, s_b, n, 16)) { // different heap offsets per rank: pull from root
+    bcast_body<uint4, UNROLL>(c, s_a, bytes, root, 0);
+  } else {
+    bcast_body<unsigned char, 1>(c, s_a, bytes, root, 0);
   }
   sync_end(c);
 }
@@ -1292,6 +1292,8 @@ bcast_nvls2_kernel(Comm c, uint64_t buf_off, size_t bytes, int root, uint32_t sh
       for (int u = 0; u < UNROLL; ++u)
         if (gi[u] < nvec) multimem_st16(dst + gi[u] * 16, v[u]);
     }
+  } else if ((bytes & 15) == 0 && all_aligned_to(s_a, s_b, n, 16)) { // different heap offsets per rank: fused P2P two-shot
+    bcast_body<uint4, UNROLL>(c, s_a, bytes, root, 1);
   } else {
     bcast_body<unsigned char, 1>(c, s_a, bytes, root, 1);
   }
@@ -1330,6 +1332,8 @@ allgather_nvls_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t bytes
         if (i < nvec) multimem_st16(dst + i * 16, v[u]);
       }
     }
+  } else if ((bytes_per_rank & 15) == 0 && all_aligned_to(s_a, s_b, n, 16)) { // different heap offsets per rank: P2P push
+    allgather_push_body<uint4, UNROLL>(c, s_a, s_b, bytes_per_rank);
   } else {
     allgather_push_body<unsigned char, 1>(c, s_a, s_b, bytes_per_rank);
   }
@@ -1465,7 +1469,11 @@ allreduce_ll_kernel(Comm c, const T* __restrict__ send, T* recv, size_t count, u
   const size_t ncell = (count + EPC - 1) / EPC;
   const uint32_t parity = seq & 1u;
   const int n = c.n;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncell; i += (size_t)gridDim.x * blockDim.x) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  // phase 1: every cell of this thread goes out to every peer before anything is waited for, so a
+  // message of many cells costs one exchange latency, not one per cell
+  for (size_t i = tid; i < ncell; i += stride) {
     T mine[EPC];
 #pragma unroll
     for (int k = 0; k < EPC; ++k) mine[k] = i * EPC + k < count ? send[i * EPC + k] : T(0);
@@ -1476,34 +1484,57 @@ allreduce_ll_kernel(Comm c, const T* __restrict__ send, T* recv, size_t count, u
       const int r = (c.rank + j) % n;
       st_cell(ll_lane(c, r, parity, c.rank) + i, cell);
     }
-    T acc[EPC];
-    for (int r = 0; r < n; ++r) { // rank order
-      T v[EPC];
-      if (r == c.rank) {
+  }
+  // phase 2: reduce the own lanes in rank order.  The n-1 cells of one element are loaded together
+  // (independent loads in flight: one L2 latency, not n-1) and re-loaded only while their flags lag.
+  for (size_t i = tid; i < ncell; i += stride) {
+    T mine[EPC];
 #pragma unroll
-        for (int k = 0; k < EPC; ++k) v[k] = mine[k];
-      } else {
-        const uint4* src = ll_lane(c, c.rank, parity, r) + i;
-        uint4 got = ld_cell(src);
-        unsigned long long t0 = 0;
-        uint32_t it = 0;
-        while (got.y != seq || got.w != seq) {
-          if ((++it & 0xfffu) == 0) {
-            const unsigned long long now = globaltimer_ns();
-            if (t0 == 0) t0 = now;
-            else if (c.timeout_ns && now - t0 > c.timeout_ns) {
-              *(volatile uint32_t*)c.status = 1u;
-              __threadfence_system();
-              break;
-            }
-          }
-          got = ld_cell(src);
-        }
-        LLCodec<T>::unpack(got.x, got.z, v);
+    for (int k = 0; k < EPC; ++k) mine[k] = i * EPC + k < count ? send[i * EPC + k] : T(0);
+    uint4 got[kMaxRanks];
+    uint32_t pending = 0;
+#pragma unroll
+    for (int r = 0; r < kMaxRanks; ++r)
+      if (r < n && r != c.rank) {
+        got[r] = ld_cell(ll_lane(c, c.rank, parity, r) + i);
+        pending |= 1u << r;
       }
+    unsigned long long t0 = 0;
+    uint32_t it = 0;
+    for (;;) {
 #pragma unroll
-      for (int k = 0; k < EPC; ++k) acc[k] = r == 0 ? v[k] : Op::template apply<T>(acc[k], v[k]);
+      for (int r = 0; r < kMaxRanks; ++r)
+        if ((pending >> r) & 1u) {
+          if (got[r].y == seq && got[r].w == seq) pending &= ~(1u << r);
+        }
+      if (!pending) break;
+#pragma unroll
+      for (int r = 0; r < kMaxRanks; ++r)
+        if ((pending >> r) & 1u) got[r] = ld_cell(ll_lane(c, c.rank, parity, r) + i);
+      if ((++it & 0xfffu) == 0) {
+        const unsigned long long now = globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        else if (c.timeout_ns && now - t0 > c.timeout_ns) {
+          *(volatile uint32_t*)c.status = 1u;
+          __threadfence_system();
+          break;
+        }
+      }
     }
+    T acc[EPC];
+#pragma unroll
+    for (int r = 0; r < kMaxRanks; ++r)
+      if (r < n) {
+        T v[EPC];
+        if (r == c.rank) {
+#pragma unroll
+          for (int k = 0; k < EPC; ++k) v[k] = mine[k];
+        } else {
+          LLCodec<T>::unpack(got[r].x, got[r].z, v);
+        }
+#pragma unroll
+        for (int k = 0; k < EPC; ++k) acc[k] = r == 0 ? v[k] : Op::template apply<T>(acc[k], v[k]);
+      }
 #pragma unroll
     for (int k = 0; k < EPC; ++k)
       if (i * EPC + k < count) recv[i * EPC + k] = acc[k];
