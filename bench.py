@@ -188,21 +188,40 @@ def nccl_comparison(lib, L, mpi, rank, n, local, sizes, send_ptr, recv_ptr):
         class UniqueId(ctypes.Structure):
             _fields_ = [("internal", ctypes.c_byte * 128)]
 
-        uid = UniqueId()
-        if rank == 0 and nccl.ncclGetUniqueId(ctypes.byref(uid)) != 0:
-            return {"unavailable": "ncclGetUniqueId failed"}
-        raw = np.frombuffer(bytes(uid), dtype=np.uint8).copy()
-        mpi.Bcast(raw, 0)  # the id travels over this library's own Bcast
-        ctypes.memmove(ctypes.byref(uid), raw.ctypes.data, 128)
-        comm = ctypes.c_void_p()
         nccl.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, UniqueId, ctypes.c_int]
-        rc = nccl.ncclCommInitRank(ctypes.byref(comm), n, uid, rank)
-        if rc != 0:
-            return {"unavailable": "ncclCommInitRank rc=%d" % rc}
+        nccl.ncclCommDestroy.argtypes = [ctypes.c_void_p]
+
+        def agree(flag):
+            a = np.array([1 if flag else 0], dtype=np.int64)
+            o = np.zeros(1, dtype=np.int64)
+            mpi.Allreduce(a, o, mpi.MIN)
+            return bool(o[0])
+
+        comm, note = None, None
+        for attempt in range(2):
+            uid = UniqueId()
+            if rank == 0 and nccl.ncclGetUniqueId(ctypes.byref(uid)) != 0:
+                return {"unavailable": "ncclGetUniqueId failed"}
+            raw = np.frombuffer(bytes(uid), dtype=np.uint8).copy()
+            mpi.Bcast(raw, 0)  # the id travels over this library's own Bcast
+            ctypes.memmove(ctypes.byref(uid), raw.ctypes.data, 128)
+            c = ctypes.c_void_p()
+            rc = nccl.ncclCommInitRank(ctypes.byref(c), n, uid, rank)
+            if agree(rc == 0):
+                comm = c
+                break
+            if rc == 0:
+                nccl.ncclCommDestroy(c)
+            note = "first ncclCommInitRank failed on some rank (rc=%d here); retried with NCCL_NVLS_ENABLE=0" % rc
+            os.environ["NCCL_NVLS_ENABLE"] = "0"
+        if comm is None:
+            return {"unavailable": "ncclCommInitRank failed twice", "note": note}
         nccl.ncclAllReduce.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         stream = ctypes.c_void_p()
         lib.b200mpi_get_stream(ctypes.byref(stream))
         out = {"version": ver.value, "sizes": {}}
+        if note:
+            out["note"] = note
         for nbytes in sizes:
             cnt = nbytes // 4
             iters, warm = (200, 20) if nbytes <= (1 << 20) else (20, 5)
@@ -221,7 +240,6 @@ def nccl_comparison(lib, L, mpi, rank, n, local, sizes, send_ptr, recv_ptr):
             t = float(o[0]) * 1e-3
             out["sizes"][str(nbytes)] = {"us": t * 1e6, "busbw_gbs": nbytes / t / 1e9 * 2 * (n - 1) / n}
         lib.b200mpi_stream_sync()
-        nccl.ncclCommDestroy.argtypes = [ctypes.c_void_p]
         nccl.ncclCommDestroy(comm)
         return out
     except Exception as e:  # noqa: BLE001

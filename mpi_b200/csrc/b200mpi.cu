@@ -1613,7 +1613,9 @@ static void apply_defaults() {
   const int n = g->ctrl.n;
   const bool nvls = g->heap.mc_base != 0;
   g->ll_max_bytes = 0;
-  if (!g->shared_device) g->ll_max_bytes = n >= 8 ? (32u << 10) : n >= 3 ? (64u << 10) : (256u << 10); // 2 GPUs: LL 12.3 us vs 14.5 (nvls) at 256 KiB
+  // device time, LL vs the best barrier kernel (profiles/r02): 2 GPUs 256 KiB 12.3 us vs 14.5; 4 GPUs 256 KiB 9.5 vs 13.2;
+  // 8 GPUs: see SUMMARY.md section 6
+  if (!g->shared_device) g->ll_max_bytes = n >= 8 ? (64u << 10) : (256u << 10);
   // Measured on 8 B200s (profiles/r02/sweep_n8_bcag_v1.jsonl, sweep_n8_hybrid_v1.jsonl): multicast
   // delivery tops out near 480-510 GB/s of ingress per GPU, below what plain P2P stores reach
   // (620-650), so above a few MiB Bcast and Allgather stay on the P2P kernels; mixing P2P traffic
