@@ -262,6 +262,7 @@ def main():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-nccl", action="store_true")
+    ap.add_argument("--nccl-deadline", type=int, default=75, help="seconds the NCCL comparison may take before it is abandoned")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -683,8 +684,6 @@ def main():
                 if kind == "device":
                     a_.free()
                     b_.free()
-        if not args.no_nccl:
-            secondary["nccl_allreduce_comparison"] = nccl_comparison(lib, L, mpi, rank, n, local, [1024, 1 << 20, S], send.ptr, recv.ptr)
 
     # keep the GPU under the same load a little longer so nvidia-smi (100 ms period) sees it:
     # the timed region itself is only K x ~0.1-0.7 ms
@@ -723,11 +722,7 @@ def main():
         cpu = {"value": sample / r["secs"] / 1e9, "unit": "GB/s", "cores": r["cores"], "kind": "port",
                "sample": "%d MiB, %d iterations, world of 1 = Send/Receive to self (gob encode + decode); the full-size run is `--impl reference`" % (sample >> 20, r["steps"]), "parity_ok": r["ok"]}
 
-    send.free()
-    recv.free()
-    mpi.Finalize()
-    if rank != 0:
-        return 0 if parity_ok in (True, None) else 1
+    rc_exit = 0 if parity_ok in (True, None) else 1
     line = {
         "metric": metric, "value": value, "unit": "GB/s", "n_gpus": n, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -744,8 +739,29 @@ def main():
         line["secondary"] = secondary
     if cpu is not None:
         line["cpu_baseline"] = cpu
+
+    # NCCL's allreduce on the same buffers: comparison line only, after every product measurement.
+    # A foreign library must not be able to cost the run its result: if it has not returned within
+    # the deadline, every rank prints what it has (rank 0: the contract line) and leaves.
+    if n > 1 and secondary is not None and not args.no_nccl:
+        def bail():
+            if rank == 0:
+                secondary["nccl_allreduce_comparison"] = {"unavailable": "NCCL did not return within %d s; abandoned" % args.nccl_deadline}
+                print(json.dumps(line), flush=True)
+            os._exit(rc_exit)
+        guard = threading.Timer(args.nccl_deadline, bail)
+        guard.daemon = True
+        guard.start()
+        secondary["nccl_allreduce_comparison"] = nccl_comparison(lib, L, mpi, rank, n, local, [1024, 1 << 20, S], send.ptr, recv.ptr)
+        guard.cancel()
+
+    send.free()
+    recv.free()
+    mpi.Finalize()
+    if rank != 0:
+        return rc_exit
     print(json.dumps(line))
-    return 0 if parity_ok in (True, None) else 1
+    return rc_exit
 
 
 if __name__ == "__main__":

@@ -251,6 +251,15 @@ struct Ctx {
   size_t bounce_chunk = 0, bounce_chunk_bytes = 4u << 20;
   int host_threads = 8;        // helper threads copying between pageable memory and the bounce ring
   CopyPool pool;
+  // Host-slice Send/Receive up to kP2PBounceBytes: device-mapped pinned bounce buffers, one copy kernel
+  // that reads / writes host memory itself, and a completion word the host spins on (no cudaMemcpy
+  // staging by the driver, no stream synchronisation).
+  static constexpr int kP2PBounces = 4;
+  static constexpr size_t kP2PBounceBytes = 4u << 20;
+  struct P2PBounce { char* host = nullptr; char* dev = nullptr; uint32_t seq = 0; bool busy = false; };
+  P2PBounce p2p_bounce[kP2PBounces];
+  std::mutex p2p_mu;
+  int p2p_fast = 1;
   // Opt-in (B200MPI_HOST_REGISTER=1 / "host_register"): pin the caller's pageable buffers in place
   // (cudaHostRegister, cached by address range) instead of bouncing them.  Only for callers whose
   // buffers stay mapped for the life of the cache (a freed and re-mapped range would alias stale
@@ -1340,6 +1349,43 @@ static int do_alltoall(const void* send, void* recv, size_t count, int dtype, in
 // ---------------------------------------------------------------------------------------------
 // point to point
 // ---------------------------------------------------------------------------------------------
+static Ctx::P2PBounce* acquire_bounce() {
+  std::lock_guard<std::mutex> l(g->p2p_mu);
+  for (auto& b : g->p2p_bounce) {
+    if (b.busy) continue;
+    if (!b.host) {
+      void* p = nullptr;
+      const size_t len = Ctx::kP2PBounceBytes + 64;
+      cudaError_t e = on_numa_node(g->gpu_numa_node, [&] { return cudaHostAlloc(&p, len, cudaHostAllocMapped); });
+      if (e != cudaSuccess || cudaHostGetDevicePointer((void**)&b.dev, p, 0) != cudaSuccess) { (void)cudaGetLastError(); if (p) cudaFreeHost(p); return nullptr; }
+      b.host = (char*)p;
+      *(volatile uint32_t*)(b.host + Ctx::kP2PBounceBytes) = 0;
+    }
+    b.busy = true;
+    return &b;
+  }
+  return nullptr;
+}
+static void release_bounce(Ctx::P2PBounce* b) {
+  std::lock_guard<std::mutex> l(g->p2p_mu);
+  b->busy = false;
+}
+// dst <- src with the copy kernel on `s`, then spin on the bounce's completion word.  One of dst / src
+// is the bounce's device mapping.  0, or an error (watchdog / launch failure).
+static int copy_and_wait(Ctx::P2PBounce* b, void* dst, const void* src, size_t bytes, cudaStream_t s) {
+  int rc = launch_copy(dst, src, bytes, s);
+  if (rc) return rc;
+  const uint32_t seq = ++b->seq;
+  flag_kernel<<<1, 1, 0, s>>>((uint32_t*)(b->dev + Ctx::kP2PBounceBytes), seq);
+  if ((rc = launch_check("flag_kernel"))) return rc;
+  volatile uint32_t* done = (volatile uint32_t*)(b->host + Ctx::kP2PBounceBytes);
+  Spinner sp(g->watchdog_ns);
+  while (*done != seq)
+    if (!sp.step()) { cudaStreamSynchronize(s); return fail(B200MPI_ERR_TIMEOUT, "p2p: copy kernel did not complete"); }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  return 0;
+}
+
 static size_t p2p_chunk(size_t bytes, int memkind) {
   // Host slices: small chunks so the sender's H2D of chunk k+1 overlaps the receiver's pull + D2H of
   // chunk k (both block their host thread for pageable memory).  Device buffers: one big chunk.
@@ -1407,6 +1453,7 @@ static int do_send(const void* buf, size_t count, int dtype, int dest, int tag, 
   size_t stage = 0;
   bool staged = false;
   cudaStream_t s = nullptr;
+  Ctx::P2PBounce* bounce = nullptr;
   rc = 0;
   if (bytes == 0 || (wait_ack && memkind == B200MPI_DEVICE && g->heap.contains(buf, bytes, off))) {
     // heap-resident: the receiver pulls straight out of the caller's buffer
@@ -1414,6 +1461,26 @@ static int do_send(const void* buf, size_t count, int dtype, int dest, int tag, 
     slot->nregions = 1;
     slot->region_off[0] = off;
     slot->posted.store(bytes, std::memory_order_relaxed);
+    slot->state.store(kPosted, std::memory_order_release);
+  } else if (memkind == B200MPI_HOST && g->p2p_fast && bytes <= Ctx::kP2PBounceBytes && (bounce = acquire_bounce()) != nullptr) {
+    // small host slice: memcpy into a mapped pinned buffer, one kernel moves it into the heap (the
+    // SMs read host memory over PCIe), the host spins on the completion word, then the whole
+    // message is posted at once
+    staged = true;
+    if (g->heap.alloc(bytes, stage)) {
+      release_bounce(bounce);
+      slot->state.store(kFree, std::memory_order_release);
+      g->sendtags[dest].remove(tag);
+      return fail(B200MPI_ERR_NOMEM, "send: symmetric heap exhausted while staging (raise B200MPI_HEAP_BYTES)");
+    }
+    memcpy(bounce->host, buf, bytes);
+    s = borrow_stream();
+    rc = copy_and_wait(bounce, (char*)g->heap.base[me] + stage, bounce->dev, bytes, s);
+    release_bounce(bounce);
+    slot->chunk_bytes = bytes;
+    slot->nregions = 1;
+    slot->region_off[0] = stage;
+    slot->posted.store(rc == 0 ? bytes : 0, std::memory_order_relaxed);
     slot->state.store(kPosted, std::memory_order_release);
   } else {
     staged = true;
@@ -1547,7 +1614,22 @@ static int do_recv(void* buf, size_t capacity, size_t* count_out, int dtype, int
   }
   size_t stage = 0, stage_len = 0;
   cudaStream_t s = nullptr;
-  if (rc == 0 && bytes) {
+  Ctx::P2PBounce* bounce = nullptr;
+  const bool whole = slot->chunk_bytes * (slot->nregions ? slot->nregions : 1) >= bytes; // every chunk has its own region, contiguous in the sender's heap
+  if (rc == 0 && bytes && memkind == B200MPI_HOST && g->p2p_fast && whole && bytes <= Ctx::kP2PBounceBytes && (bounce = acquire_bounce()) != nullptr) {
+    // small message into a host slice: wait until all of it is posted, ONE kernel pulls it over
+    // NVLink straight into a mapped pinned buffer (the SMs write host memory), spin, memcpy out
+    Spinner sp(g->watchdog_ns);
+    while (slot->posted.load(std::memory_order_acquire) < bytes)
+      if (!sp.step()) { rc = fail(B200MPI_ERR_TIMEOUT, "recv: sender stalled"); break; }
+    if (rc == 0) {
+      s = borrow_stream();
+      rc = copy_and_wait(bounce, bounce->dev, (const char*)g->heap.base[src] + slot->region_off[0], bytes, s);
+      if (rc == 0) memcpy(buf, bounce->host, bytes);
+      slot->done.store(bytes, std::memory_order_release);
+    }
+    release_bounce(bounce);
+  } else if (rc == 0 && bytes) {
     s = borrow_stream();
     const size_t chunk = slot->chunk_bytes;
     const size_t nreg = slot->nregions ? slot->nregions : 1;
@@ -1615,7 +1697,8 @@ static void apply_defaults() {
   g->ll_max_bytes = 0;
   // device time, LL vs the best barrier kernel (profiles/r02): 2 GPUs 256 KiB 12.3 us vs 14.5; 4 GPUs 256 KiB 9.5 vs 13.2;
   // 8 GPUs: see SUMMARY.md section 6
-  if (!g->shared_device) g->ll_max_bytes = n >= 8 ? (64u << 10) : (256u << 10);
+  // 8 GPUs (two-phase kernel): 1 KiB 6.9 us vs 12.7, 32 KiB 8.6 vs 12.7, 256 KiB 12.9 vs 15.3 -> LL over its whole range
+  if (!g->shared_device) g->ll_max_bytes = std::min<size_t>(256u << 10, ll_cells(n) * 8);
   // Measured on 8 B200s (profiles/r02/sweep_n8_bcag_v1.jsonl, sweep_n8_hybrid_v1.jsonl): multicast
   // delivery tops out near 480-510 GB/s of ingress per GPU, below what plain P2P stores reach
   // (620-650), so above a few MiB Bcast and Allgather stay on the P2P kernels; mixing P2P traffic
@@ -1761,6 +1844,7 @@ int b200mpi_finalize(void) {
     if (g->ev1) cudaEventDestroy(g->ev1);
     if (g->status_host) cudaFreeHost(g->status_host);
     if (g->ll_host) cudaFreeHost(g->ll_host);
+    for (auto& b : g->p2p_bounce) if (b.host) cudaFreeHost(b.host);
     if (g->pool.running()) g->pool.shutdown();
     if (g->bounce) cudaFreeHost(g->bounce);
     for (auto& e : g->registered) cudaHostUnregister((void*)e.first);
@@ -2001,7 +2085,17 @@ int b200mpi_set_param(const char* name, int64_t value) {
   else if (k == "bcast_nvls2") g->bcast_nvls2 = value ? 1 : 0;
   else if (k == "bcast_nvls_min") g->bcast_nvls_min = (size_t)std::max<int64_t>(value, 0);
   else if (k == "allgather_nvls_min") g->allgather_nvls_min = (size_t)std::max<int64_t>(value, 0);
-  else if (k == "host_register") g->host_register = value ? 1 : 0;
+  else if (k == "host_register") {
+    g->host_register = value ? 1 : 0;
+    if (!value) { // leaving the mode drops every cached registration: the caller may free those buffers now
+      cudaStreamSynchronize(g->h2d_stream);
+      cudaStreamSynchronize(g->d2h_stream);
+      for (auto& e : g->registered) cudaHostUnregister((void*)e.first);
+      g->registered.clear();
+      (void)cudaGetLastError();
+    }
+  }
+  else if (k == "p2p_fast") g->p2p_fast = value ? 1 : 0;
   else if (k == "bounce_chunk_bytes") g->bounce_chunk_bytes = (size_t)std::max<int64_t>(value, 65536);
   else if (k == "host_threads") { if (g->pool.running()) return fail(B200MPI_ERR_ARG, "set_param: host_threads must be set before the first pageable host-slice call"); g->host_threads = (int)std::max<int64_t>(value, 0); }
   else return fail(B200MPI_ERR_ARG, "set_param: unknown parameter '" + k + "'");

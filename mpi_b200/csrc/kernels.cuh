@@ -1556,6 +1556,13 @@ allreduce_ll_kernel(Comm c, const T* __restrict__ send, T* recv, size_t count, u
   }
 }
 
+// Completion word for host-polled copies: enqueued right behind a copy kernel on the same stream, so
+// the copy's stores (possibly into mapped host memory) are complete when the word becomes visible.
+__global__ void flag_kernel(uint32_t* done, uint32_t value) {
+  __threadfence_system();
+  *(volatile uint32_t*)done = value;
+}
+
 // A device-wide rendezvous with nothing in between (b200mpi_barrier).
 __global__ void barrier_kernel(Comm c) {
   __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
