@@ -131,6 +131,27 @@ def measured_traffic(n, nbytes, kernel):
     return None, None
 
 
+def nvlink_counters(gpu):
+    """Sum of the per-link NVLink data counters of one GPU (`nvidia-smi nvlink -gt d`), in bytes:
+    (tx, rx), or None when the tool or the counters are not there.  ncu cannot read the NVLink
+    counters on this pool, so this is the only hardware count of link bytes."""
+    import re
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(gpu)], capture_output=True, text=True, timeout=20).stdout
+        tx = rx = 0
+        seen = False
+        for m in re.finditer(r"Data\s+(Tx|Rx)\s*:\s*(\d+)\s*(KiB|KB|MiB|B)?", out):
+            mult = {"KiB": 1024, "KB": 1000, "MiB": 1 << 20, "B": 1, None: 1024}[m.group(3)]
+            if m.group(1) == "Tx":
+                tx += int(m.group(2)) * mult
+            else:
+                rx += int(m.group(2)) * mult
+            seen = True
+        return (tx, rx) if seen else None
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -685,6 +706,22 @@ def main():
                     a_.free()
                     b_.free()
 
+    # hardware count of link bytes for the timed call (rank 0's GPU): counters before / after 50 more steps
+    nvl = None
+    if n > 1:
+        mpi.Barrier()
+        c0 = nvlink_counters(local) if rank == 0 else None
+        mpi.Barrier()
+        run_steps(50)
+        if lib.b200mpi_stream_sync():
+            raise RuntimeError(L.last_error())
+        mpi.Barrier()
+        c1 = nvlink_counters(local) if rank == 0 else None
+        if c0 and c1:
+            nvl = {"tx_bytes_per_step": (c1[0] - c0[0]) / 50.0, "rx_bytes_per_step": (c1[1] - c0[1]) / 50.0,
+                   "tx_gbs": (c1[0] - c0[0]) / 50.0 / t_step / 1e9, "rx_gbs": (c1[1] - c0[1]) / 50.0 / t_step / 1e9,
+                   "source": "nvidia-smi nvlink -gt d on rank 0's GPU around 50 more steps of the timed call (includes protocol overhead the counters see)"}
+
     # keep the GPU under the same load a little longer so nvidia-smi (100 ms period) sees it:
     # the timed region itself is only K x ~0.1-0.7 ms
     n_load = int(min(max(0.6 / t_step, 10), 20000))  # same count on every rank (t_step is the max over ranks)
@@ -710,6 +747,8 @@ def main():
                 "algorithmic_bytes_per_launch": 2.0 * (n - 1) / n * S,
                 "hbm": {"achieved": hbm_bytes / t_step / 1e9, "peak": hbm_peak, "frac": hbm_bytes / t_step / 1e9 / hbm_peak, "peak_source": peak_kind}}
 
+    if n > 1:
+        roof["nvlink_counters"] = nvl
     traffic, tsrc = measured_traffic(n, S, roof["kernel"])
     if traffic is not None:
         roof["traffic"] = traffic
