@@ -1706,6 +1706,10 @@ static void apply_defaults() {
   g->bcast_nvls_min = SIZE_MAX;
   g->allgather_nvls_min = SIZE_MAX;
   g->hybrid_p2p_permille = 0;
+  // ranks time-slicing one GPU (functional-test mode): every extra kernel costs a time slice, keep the
+  // host-slice Send/Receive on the copy-engine path there
+  g->p2p_fast = g->shared_device ? 0 : 1;
+  if (const char* w = getenv("B200MPI_P2P_FAST")) g->p2p_fast = atoi(w) != 0;
   (void)nvls;
   if (const char* w = getenv("B200MPI_LL_MAX")) g->ll_max_bytes = std::min<size_t>(strtoull(w, nullptr, 0), ll_cells(g->ctrl.n) * 8);
   if (const char* w = getenv("B200MPI_HYBRID_PERMILLE")) g->hybrid_p2p_permille = std::max(0, std::min(900, atoi(w)));
