@@ -138,7 +138,11 @@ __device__ __forceinline__ bool wait_cells(const Slot* s, uint32_t epoch, const 
   uint32_t it = 0;
   for (;;) {
     const uint4 x = ld_cell16(&s->cell[0]), y = ld_cell16(&s->cell[1]), z = ld_cell16(&s->cell[2]);
-    if (x.y == epoch && x.w == epoch && y.y == epoch && y.w == epoch && z.y == epoch && z.w == epoch) {
+    // >= (wrap-safe), not ==: in normal operation a peer is never ahead (it waits for this CTA at its end
+    // barrier), so the two are the same; after a failed call a peer may already be announcing its next
+    // one, and a late CTA must then see "newer, different signature" at once instead of spinning.
+    if ((int32_t)(x.y - epoch) >= 0 && (int32_t)(x.w - epoch) >= 0 && (int32_t)(y.y - epoch) >= 0 && (int32_t)(y.w - epoch) >= 0 &&
+        (int32_t)(z.y - epoch) >= 0 && (int32_t)(z.w - epoch) >= 0) {
       a = ((uint64_t)x.z << 32) | x.x;
       b = ((uint64_t)y.z << 32) | y.x;
       sig = ((uint64_t)z.z << 32) | z.x;
@@ -156,11 +160,19 @@ __device__ __forceinline__ bool wait_cells(const Slot* s, uint32_t epoch, const 
   }
 }
 
+// Why sync_start said no, for sync_end_failed: 0 fine, 1 this CTA's partner announced a different
+// signature (the partner exists and fails the same way), 2 a peer's CTA 0 announced a different
+// signature (grids may differ: this CTA may have no partner at all), 3 watchdog.
+__device__ __forceinline__ int* start_verdict() {
+  __shared__ int verdict;
+  return &verdict;
+}
+
 __device__ __forceinline__ bool sync_start(const Comm& c, uint64_t a, uint64_t b, uint64_t* s_a,
                                            uint64_t* s_b) {
-  __shared__ int s_bad;
+  int* verdict = start_verdict();
   const int t = threadIdx.x;
-  if (t == 0) s_bad = 0;
+  if (t == 0) *verdict = 0;
   __syncthreads();
   if (t < c.n) {
     Slot* theirs = slot_of(c, t, blockIdx.x, c.rank);
@@ -170,21 +182,22 @@ __device__ __forceinline__ bool sync_start(const Comm& c, uint64_t a, uint64_t b
     bool ok = true;
     uint64_t pa, pb, psig;
     if (blockIdx.x != 0) {
-      if (!wait_cells(slot_of(c, c.rank, 0, t), c.epoch, c, pa, pb, psig)) { s_bad = 2; ok = false; }
-      else if (psig != c.sig) { s_bad = 1; ok = false; }
+      if (!wait_cells(slot_of(c, c.rank, 0, t), c.epoch, c, pa, pb, psig)) { atomicMax(verdict, 3); ok = false; }
+      else if (psig != c.sig) { atomicMax(verdict, 2); ok = false; }
     }
     if (ok) {
-      if (!wait_cells(slot_of(c, c.rank, blockIdx.x, t), c.epoch, c, pa, pb, psig)) s_bad = 2;
+      if (!wait_cells(slot_of(c, c.rank, blockIdx.x, t), c.epoch, c, pa, pb, psig)) atomicMax(verdict, 3);
       else {
         s_a[t] = pa;
         s_b[t] = pb;
-        if (psig != c.sig) s_bad = 1;
+        if (psig != c.sig) atomicMax(verdict, 1);
       }
     }
   }
   __syncthreads();
-  if (s_bad) {
-    if (t == 0 && s_bad == 1) {
+  const int v = *verdict;
+  if (v) {
+    if (t == 0 && v != 3) { // a watchdog expiry has already raised status 1
       *(volatile uint32_t*)c.status = 2u;
       __threadfence_system();
     }
@@ -201,6 +214,21 @@ __device__ __forceinline__ void sync_end(const Comm& c) {
   if (t < c.n) {
     st_release_sys(&slot_of(c, t, blockIdx.x, c.rank)->flag, c.end_epoch);
     wait_flag(&slot_of(c, c.rank, blockIdx.x, t)->flag, c.end_epoch, c);
+  }
+}
+
+// The way out of a kernel whose sync_start said no (the body was skipped, nothing of this CTA is in
+// flight).  The end flag is always signalled, so a partner that is waiting gets released; this CTA
+// itself waits only when it knows a partner exists and left the same way (verdict 1) -- a CTA that
+// learnt about the mismatch from the peers' CTA 0, or that timed out, may have no partner, and
+// waiting for one would stall until the watchdog.
+__device__ __forceinline__ void sync_end_failed(const Comm& c) {
+  __syncthreads();
+  const int t = threadIdx.x;
+  const bool wait = *start_verdict() == 1;
+  if (t < c.n) {
+    st_release_sys(&slot_of(c, t, blockIdx.x, c.rank)->flag, c.end_epoch);
+    if (wait) wait_flag(&slot_of(c, c.rank, blockIdx.x, t)->flag, c.end_epoch, c);
   }
 }
 
@@ -310,7 +338,7 @@ allreduce_oneshot_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t co
   __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
   const bool call_ok = sync_start(c, send_off, recv_off, s_a, s_b);
   if (!call_ok) { // ranks disagree about this call: touch nothing, leave through the end barrier
-    sync_end(c);
+    sync_end_failed(c);
     return;
   }
   const int n = NR ? NR : c.n;
@@ -362,7 +390,7 @@ allreduce_oneshot_shfl_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size
   __shared__ const char* s_src[kMaxRanks];
   const bool call_ok = sync_start(c, send_off, recv_off, s_a, s_b);
   if (!call_ok) { // ranks disagree about this call: touch nothing, leave through the end barrier
-    sync_end(c);
+    sync_end_failed(c);
     return;
   }
   if (threadIdx.x < NR) s_src[threadIdx.x] = c.base[threadIdx.x] + s_a[threadIdx.x];
@@ -533,7 +561,7 @@ allreduce_twoshot_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t co
   __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
   const bool call_ok = sync_start(c, send_off, recv_off, s_a, s_b);
   if (!call_ok) { // ranks disagree about this call: touch nothing, leave through the end barrier
-    sync_end(c);
+    sync_end_failed(c);
     return;
   }
   twoshot_body<T, Op, NR, UNROLL>(c, s_a, s_b, count, shift, blockIdx.x, gridDim.x, only_dst);
@@ -597,7 +625,7 @@ allreduce_twoshot_smem_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size
   unsigned char* out_tiles = smem_raw + (size_t)kSmemStages * NR * kSmemChunk; // [ostage][chunk]
   const bool call_ok = sync_start(c, send_off, recv_off, s_a, s_b);
   if (!call_ok) { // ranks disagree about this call: touch nothing, leave through the end barrier
-    sync_end(c);
+    sync_end_failed(c);
     return;
   }
   constexpr int EPV = Pack<T>::N;
@@ -707,7 +735,7 @@ allreduce_ring_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t count
   __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
   const bool call_ok = sync_start(c, send_off, recv_off, s_a, s_b);
   if (!call_ok) { // ranks disagree about this call: touch nothing, leave through the end barrier
-    sync_end(c);
+    sync_end_failed(c);
     return;
   }
   const int n = c.n, r = c.rank;
@@ -881,7 +909,7 @@ allreduce_nvls_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t count
   __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
   const bool call_ok = sync_start(c, send_off, recv_off, s_a, s_b);
   if (!call_ok) { // ranks disagree about this call: touch nothing, leave through the end barrier
-    sync_end(c);
+    sync_end_failed(c);
     return;
   }
   constexpr int EPV = Pack<T>::N;
@@ -918,7 +946,7 @@ allreduce_hybrid_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t cou
   __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks], s_a2[kMaxRanks], s_b2[kMaxRanks];
   const bool call_ok = sync_start(c, send_off, recv_off, s_a, s_b);
   if (!call_ok) {
-    sync_end(c);
+    sync_end_failed(c);
     return;
   }
   constexpr int EPV = Pack<T>::N;
@@ -952,7 +980,7 @@ reduce_scatter_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t count
   __shared__ const char* src[kMaxRanks];
   const bool call_ok = sync_start(c, send_off, recv_off, s_a, s_b);
   if (!call_ok) {
-    sync_end(c);
+    sync_end_failed(c);
     return;
   }
   const int n = c.n;
@@ -996,7 +1024,7 @@ reduce_scatter_nvls_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t 
   __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
   const bool call_ok = sync_start(c, send_off, recv_off, s_a, s_b);
   if (!call_ok) {
-    sync_end(c);
+    sync_end_failed(c);
     return;
   }
   const int n = c.n;
@@ -1093,7 +1121,7 @@ allgather_push_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t bytes
   __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
   const bool call_ok = sync_start(c, send_off, recv_off, s_a, s_b);
   if (!call_ok) { // ranks disagree about this call: touch nothing, leave through the end barrier
-    sync_end(c);
+    sync_end_failed(c);
     return;
   }
   if (sizeof(U) == 1 || all_aligned_to(s_a, s_b, c.n, sizeof(U))) allgather_push_body<U, UNROLL>(c, s_a, s_b, bytes_per_rank);
@@ -1138,7 +1166,7 @@ allgather_ring_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t bytes
   __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
   const bool call_ok = sync_start(c, send_off, recv_off, s_a, s_b);
   if (!call_ok) { // ranks disagree about this call: touch nothing, leave through the end barrier
-    sync_end(c);
+    sync_end_failed(c);
     return;
   }
   if (sizeof(U) == 1 || all_aligned_to(s_a, s_b, c.n, sizeof(U))) allgather_ring_body<U>(c, s_a, s_b, bytes_per_rank);
@@ -1205,7 +1233,7 @@ bcast_kernel(Comm c, uint64_t buf_off, size_t bytes, int root, int mode) {
   __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
   const bool call_ok = sync_start(c, buf_off, buf_off, s_a, s_b);
   if (!call_ok) { // ranks disagree about this call: touch nothing, leave through the end barrier
-    sync_end(c);
+    sync_end_failed(c);
     return;
   }
   if (sizeof(U) == 1 || all_aligned_to(s_a, s_b, c.n, sizeof(U))) bcast_body<U, UNROLL>(c, s_a, bytes, root, mode);
@@ -1220,7 +1248,7 @@ bcast_nvls_kernel(Comm c, uint64_t buf_off, size_t bytes, int root) {
   __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
   const bool call_ok = sync_start(c, buf_off, buf_off, s_a, s_b);
   if (!call_ok) { // ranks disagree about this call: touch nothing, leave through the end barrier
-    sync_end(c);
+    sync_end_failed(c);
     return;
   }
   const int n = c.n;
@@ -1266,7 +1294,7 @@ bcast_nvls2_kernel(Comm c, uint64_t buf_off, size_t bytes, int root, uint32_t sh
   __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
   const bool call_ok = sync_start(c, buf_off, buf_off, s_a, s_b);
   if (!call_ok) {
-    sync_end(c);
+    sync_end_failed(c);
     return;
   }
   const int n = c.n;
@@ -1308,7 +1336,7 @@ allgather_nvls_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t bytes
   __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
   const bool call_ok = sync_start(c, send_off, recv_off, s_a, s_b);
   if (!call_ok) {
-    sync_end(c);
+    sync_end_failed(c);
     return;
   }
   const int n = c.n;
@@ -1375,7 +1403,7 @@ alltoall_kernel(Comm c, uint64_t send_off, uint64_t recv_off, size_t bytes_per_b
   __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
   const bool call_ok = sync_start(c, send_off, recv_off, s_a, s_b);
   if (!call_ok) {
-    sync_end(c);
+    sync_end_failed(c);
     return;
   }
   if (sizeof(U) == 1 || all_aligned_to(s_a, s_b, c.n, sizeof(U))) alltoall_body<U, UNROLL>(c, s_a, s_b, bytes_per_block);
@@ -1566,8 +1594,8 @@ __global__ void flag_kernel(uint32_t* done, uint32_t value) {
 // A device-wide rendezvous with nothing in between (b200mpi_barrier).
 __global__ void barrier_kernel(Comm c) {
   __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
-  (void)sync_start(c, 0, 0, s_a, s_b);
-  sync_end(c);
+  if (sync_start(c, 0, 0, s_a, s_b)) sync_end(c);
+  else sync_end_failed(c);
 }
 
 } // namespace b200
