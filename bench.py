@@ -587,7 +587,7 @@ def main():
         if rank == 0:
             print(json.dumps(core), flush=True)
         os._exit(0 if parity_ok in (True, None) else 1)
-    deadline = threading.Timer(max(30.0, args.deadline - (time.time() - t_start)), deadline_bail)
+    deadline = threading.Timer(max(1.0, args.deadline - (time.time() - t_start)), deadline_bail)
     deadline.daemon = True
     deadline.start()
 
