@@ -13,22 +13,30 @@ WORKER = os.path.join(ROOT, "tests", "_worker.py")
 
 
 def free_ports(n):
-    """n consecutive-looking free TCP ports with the same number of digits (sorted order == rank order)."""
-    socks, ports = [], []
-    base = None
-    for _ in range(200):
+    """n consecutive free TCP ports with the same number of digits (sorted order == rank order).
+    Every one of them is bound once here, so a port some other process holds is never handed out."""
+    for _ in range(400):
         s = socket.socket()
         s.bind(("127.0.0.1", 0))
-        p = s.getsockname()[1]
+        base = s.getsockname()[1]
         s.close()
-        if 20000 <= p <= 60000 - n:
-            base = p
-            break
-    if base is None:
-        base = 23456
-    for i in range(n):
-        ports.append(base + i)
-    return ports
+        if not (20000 <= base <= 60000 - n):
+            continue
+        held = []
+        try:
+            for i in range(n):
+                t = socket.socket()
+                t.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+                t.bind(("127.0.0.1", base + i))
+                held.append(t)
+        except OSError:
+            continue
+        finally:
+            for t in held:
+                t.close()
+        if len(held) == n:
+            return [base + i for i in range(n)]
+    raise RuntimeError("no run of %d free ports found" % n)
 
 
 def run_world(n, scenario, args=(), env=None, timeout=600, gpus_shared=True, extra_flags=(), per_rank_env=None):
