@@ -24,8 +24,11 @@ needed between steps.
             Bcast S from the first and the last rank, Allgather i64 1 Mi per rank, ReduceScatter,
             a 1 MiB float64 ping-pong.  Any mismatch: the flag is false and the exit code is 1.
   secondary N >= 2: Bcast S busbw, Allgather (1 Mi int64 per rank) busbw, 1 MiB float64 bounce
-            round trip, 1 KiB Allreduce latency, NCCL's allreduce on the same buffers (comparison
-            line only; NCCL is never on the product path).
+            round trip, 1 KiB / 32 KiB / 1 MiB Allreduce latency, the link ceilings measured in the
+            same job (b200mpi_link_probe: one direction busy, both directions busy), NCCL's allreduce
+            on the same buffers (comparison line only, run last and under a deadline; NCCL is never
+            on the product path).  roofline.nvlink_counters: hardware link byte counts
+            (nvidia-smi nvlink) around 50 more steps of the timed call, when the tool exposes them.
   roofline  N == 1: HBM (read S + write S per launch) against MEASURED_PEAKS.json hbm_gbs;
             N >= 2: NVLink, busbw against 900 GB/s nominal (measured peer copy ~770 GB/s) plus the
             HBM side ((3 - 1/N) * S per launch).
@@ -728,6 +731,24 @@ def main():
                 if kind == "device":
                     a_.free()
                     b_.free()
+
+    # what the links deliver to this library's plain copy kernel, measured in the same job: the ceilings
+    # the busbw above is held against (one direction busy / both directions busy)
+    if secondary is not None:
+        tot, used = ctypes.c_size_t(), ctypes.c_size_t()
+        lib.b200mpi_heap_info(ctypes.byref(tot), ctypes.byref(used), None)
+        if all_ranks(tot.value - used.value >= 2 * S + (64 << 20)):
+            probe = {}
+            for mode, name in ((2, "rank0_pulls_other_direction_idle"), (3, "rank0_pushes_other_direction_idle"), (0, "all_ranks_pull"),
+                               (1, "all_ranks_push"), (4, "all_ranks_pull_and_push")):
+                pm = ctypes.c_float()
+                if lib.b200mpi_link_probe(S, mode, 5, ctypes.byref(pm)):
+                    probe = {"error": L.last_error()}
+                    break
+                tp = max_over_ranks(pm.value * 1e-3)
+                probe[name] = ((2 if mode == 4 else 1) * S / tp / 1e9) if tp > 0 else None
+            secondary["link_probe_gbs_per_direction"] = probe
+            secondary["link_probe_note"] = "b200mpi_link_probe: copy_bytes_kernel between rank r and r+1, %d MiB, 5 iterations, slowest rank" % (S >> 20)
 
     # hardware count of link bytes for the timed call (rank 0's GPU): counters before / after 50 more steps
     nvl = None

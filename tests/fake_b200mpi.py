@@ -182,6 +182,12 @@ class FakeLib:
         _out(up).value, _out(down).value, _out(both).value = 50.0, 50.0, 40.0
         return 0
 
+    def b200mpi_link_probe(self, nbytes, mode, iters, ms):
+        if self.dist is not None:
+            self.dist.barrier()
+        _out(ms).value = nbytes / 700e9 * 1e3 * (2 if mode == 4 else 1)
+        return 0
+
     # ---- transport helpers -------------------------------------------------------------------------
     def _gather(self, arr):
         import torch

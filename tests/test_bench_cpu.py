@@ -76,6 +76,8 @@ def test_bench_world_of_2_parity_dict_and_secondary():
     sec = d["secondary"]
     assert sec["bcast_4MiB_busbw_gbs"] > 0 and sec["allgather_1Mi_i64_busbw_gbs"] > 0 and sec["bounce_1MiB_f64_rt_us_host"] > 0
     assert d["roofline"]["bound"] == "nvlink" and "nvlink_counters" in d["roofline"]
+    assert set(sec["link_probe_gbs_per_direction"]) == {"rank0_pulls_other_direction_idle", "rank0_pushes_other_direction_idle", "all_ranks_pull",
+                                                        "all_ranks_push", "all_ranks_pull_and_push"}
     assert d["e2e"]["frac_of_roofline"] > 0
 
 
