@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B200MPI_VERSION 100 /* 0.1.0 */
+#define B200MPI_VERSION 200 /* 0.2.0: + isend/wait, reduce_scatter, reduce, alltoall, probes, get_param (additive) */
 #define B200MPI_MAX_RANKS 8 /* "the 8 GPUs of one box" */
 
 typedef enum {

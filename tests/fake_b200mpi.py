@@ -87,7 +87,7 @@ class FakeLib:
         return 0
 
     def b200mpi_version(self):
-        return 100
+        return 200
 
     def b200mpi_last_error(self):
         return self.err

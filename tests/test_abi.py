@@ -59,7 +59,7 @@ def test_library_contains_sm_100a_code_only():
 
 def test_before_init_matches_reference_conventions():
     lib = mpi.load()
-    assert lib.b200mpi_version() == 100
+    assert lib.b200mpi_version() == 200
     assert mpi.Rank() == -1 and mpi.Size() == 0  # mpi.go:110-118
     assert lib.b200mpi_device() == -1
     p = ctypes.c_void_p()
