@@ -164,7 +164,8 @@ int b200mpi_set_max_blocks(int blocks); /* cap grid size (0 = default: SMs x occ
  * "nvls_max_blocks", "oneshot_max_bytes", "ll_max_bytes", "stage_chunk", "pipe_min_bytes",
  * "pipe_chunk_bytes", "bounce_chunk_bytes", "host_threads", "own_block_bytes", "copy_variant",
  * "hybrid_p2p_permille", "hybrid_p2p_blocks", "hybrid_min_bytes", "bcast_nvls2", "bcast_nvls_min",
- * "allgather_nvls_min". */
+ * "allgather_nvls_min", "host_register" (pin pageable host slices in place, cached; 0 drops the cache),
+ * "p2p_fast" (host-slice Send/Receive through mapped pinned buffers), "watchdog_ms". */
 int b200mpi_set_param(const char* name, int64_t value);
 int b200mpi_get_param(const char* name, int64_t* value); /* also "sm_count", "shared_device" (read only) */
 /* cudaStream_t used for collectives; set NULL to restore the library's own stream. */
