@@ -458,13 +458,13 @@ struct Owner {
   size_t slots;  // upper bound of this rank's local vector slots: (blocks owned) << shift
   uint32_t shift;
   int n, rank;
-  __device__ __forceinline__ Owner(size_t nvec_, uint32_t shift_, int n_, int rank_) : nvec(nvec_), shift(shift_), n(n_), rank(rank_) {
+  __host__ __device__ __forceinline__ Owner(size_t nvec_, uint32_t shift_, int n_, int rank_) : nvec(nvec_), shift(shift_), n(n_), rank(rank_) {
     const size_t nblk = (nvec_ + ((size_t)1 << shift_) - 1) >> shift_;
     const size_t mine = nblk > (size_t)rank_ ? (nblk - rank_ + n_ - 1) / n_ : 0;
     slots = mine << shift_;
   }
   // local slot -> global vector index (may be >= nvec in the last, partial block)
-  __device__ __forceinline__ size_t global(size_t slot) const {
+  __host__ __device__ __forceinline__ size_t global(size_t slot) const {
     const size_t q = slot >> shift, w = slot & (((size_t)1 << shift) - 1);
     return ((q * n + rank) << shift) + w;
   }
