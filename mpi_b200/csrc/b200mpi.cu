@@ -130,8 +130,11 @@ template <typename F>
 static auto on_numa_node(int node, F fn) -> decltype(fn()) {
   cpu_set_t want, old;
   const bool have = cpus_of_node(node, want) && sched_getaffinity(0, sizeof old, &old) == 0;
-  unsigned long mask[16] = {0};
+  unsigned long mask[16] = {0}, old_mask[16] = {0};
+  int old_mode = 0;
+  bool have_policy = false;
   if (have) {
+    have_policy = syscall(SYS_get_mempolicy, &old_mode, old_mask, sizeof old_mask * 8, nullptr, 0) == 0;
     if (node < (int)(sizeof mask * 8)) mask[node / (8 * sizeof(long))] |= 1ul << (node % (8 * sizeof(long)));
     syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, sizeof mask * 8);
     // only narrow the affinity: a caller pinned elsewhere (taskset, cgroup cpuset) stays where it is
@@ -141,7 +144,9 @@ static auto on_numa_node(int node, F fn) -> decltype(fn()) {
   }
   auto r = fn();
   if (have) {
-    syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0);
+    // back to what the caller had (MPOL_DEFAULT when it could not be read)
+    if (have_policy && old_mode != 0) syscall(SYS_set_mempolicy, old_mode, old_mask, sizeof old_mask * 8);
+    else syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0);
     sched_setaffinity(0, sizeof old, &old);
   }
   return r;
@@ -398,11 +403,14 @@ static Comm next_comm() {
 // paths) or LL calls: agree on max(epoch), max(ll_seq) over the control plane before the next call.
 // Every rank sees the failure of a mismatched call (sync_start compares all signatures on every
 // rank), so every rank comes here.
-static void resync_after_error() {
+static void resync_after_error(bool peers_alive) {
   if (g->ctrl.n == 1) return;
   struct { uint32_t epoch, ll_seq; } mine = {g->epoch, g->ll_seq}, all[B200MPI_MAX_RANKS];
   std::string err;
-  if (g->ctrl.allgather(&mine, sizeof mine, all, err) != 0) return; // a dead peer: nothing to agree with
+  // A mismatched call ends on every rank, so everybody comes here and the exchange is prompt.  After
+  // a watchdog expiry a peer may be gone or stuck: do not trade one hang for another.
+  const int64_t wait_ns = peers_alive ? 30ll * 1000000000ll : 2ll * 1000000000ll;
+  if (g->ctrl.allgather(&mine, sizeof mine, all, err, wait_ns) != 0) return; // nothing to agree with
   for (int r = 0; r < g->ctrl.n; ++r) {
     if ((int32_t)(all[r].epoch - g->epoch) > 0) g->epoch = all[r].epoch;
     if ((int32_t)(all[r].ll_seq - g->ll_seq) > 0) g->ll_seq = all[r].ll_seq;
@@ -415,7 +423,7 @@ static int check_status() {
   if (g->status_host && *(volatile uint32_t*)g->status_host) {
     const uint32_t st = *(volatile uint32_t*)g->status_host;
     *(volatile uint32_t*)g->status_host = 0;
-    resync_after_error();
+    resync_after_error(st == 2u);
     if (st == 2u) return fail(B200MPI_ERR_PEER, "mismatched collective: ranks disagree on the call (collective, count, dtype, op, root, algorithm or grid); buffers were left untouched");
     return fail(B200MPI_ERR_TIMEOUT, "device-side watchdog: a peer did not reach the collective in time");
   }
@@ -1103,6 +1111,12 @@ static int host_pipeline(const PipeSpec& sp) {
   char* b_out = g->bounce ? g->bounce + (size_t)R * g->bounce_chunk : nullptr;
   std::atomic<int> pend_in[Ctx::kBounceSlots], pend_out[Ctx::kBounceSlots];
   for (int i = 0; i < R; ++i) { pend_in[i].store(0); pend_out[i].store(0); }
+  // queued copy tasks point at these counters: whatever way this function is left (CUDA error paths
+  // included), the helper threads are done with them first
+  struct Drain {
+    CopyPool& pool; std::atomic<int>* a; std::atomic<int>* b; int n; bool on;
+    ~Drain() { if (on) for (int i = 0; i < n; ++i) { pool.wait(a[i]); pool.wait(b[i]); } }
+  } drain{g->pool, pend_in, pend_out, R, bounce};
   auto lo_of = [&](size_t k) { return k * chunk_elems; };
   auto len_of = [&](size_t k) { return std::min(chunk_elems, sp.count - lo_of(k)); };
 

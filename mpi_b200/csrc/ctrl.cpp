@@ -491,7 +491,7 @@ void Ctrl::shutdown() { // network.go:354-369
   }
 }
 
-int Ctrl::allgather(const void* mine, size_t bytes, void* all, std::string& err) {
+int Ctrl::allgather(const void* mine, size_t bytes, void* all, std::string& err, int64_t wait_ns) {
   char* out = (char*)all;
   memcpy(out + (size_t)rank * bytes, mine, bytes);
   if (n == 1) return 0;
@@ -503,7 +503,7 @@ int Ctrl::allgather(const void* mine, size_t bytes, void* all, std::string& err)
       return B200MPI_ERR_PEER;
     }
   }
-  Deadline dl(timeout_ns > 0 ? std::max<int64_t>(timeout_ns, 60000000000ll) : 0);
+  Deadline dl(wait_ns >= 0 ? std::max<int64_t>(wait_ns, 1) : (timeout_ns > 0 ? std::max<int64_t>(timeout_ns, 60000000000ll) : 0));
   for (int p = 0; p < n; ++p) {
     if (p == rank) continue;
     int r = read_full(listen_fd[p], out + (size_t)p * bytes, bytes, dl);

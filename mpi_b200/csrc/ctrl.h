@@ -31,8 +31,9 @@ struct Ctrl {
            std::string& err);
   void shutdown();
 
-  // Every rank contributes `bytes`; all[r*bytes ...] = rank r's blob.
-  int allgather(const void* mine, size_t bytes, void* all, std::string& err);
+  // Every rank contributes `bytes`; all[r*bytes ...] = rank r's blob.  wait_ns < 0: the init
+  // timeout rule (forever when -mpi-inittimeout is 0); otherwise give up after wait_ns.
+  int allgather(const void* mine, size_t bytes, void* all, std::string& err, int64_t wait_ns = -1);
   int barrier(std::string& err);
   // out[r] = a descriptor in this process for rank r's fd (out[rank] = dup(myfd)).
   int alltoall_fd(int myfd, std::vector<int>& out, std::string& err);
