@@ -138,3 +138,34 @@ def test_more_than_eight_ranks_rejected():
     addrs = ",".join(":%d" % (7100 + i) for i in range(9))
     out = _out(_init(":7100", addrs))
     assert "RC -3" in out and "at most 8" in out
+
+
+# ---- the collectives added along the reference's conventions: argument checks before any device work --------
+def test_new_collectives_check_shapes_before_touching_the_library():
+    c = mpi.Cuda()
+    a4, a8 = np.zeros(4, dtype=np.float32), np.zeros(8, dtype=np.float32)
+    with pytest.raises(ValueError):
+        c.Allreduce(a4, a8)                       # lengths differ
+    with pytest.raises(ValueError):
+        c.Allreduce(a4, np.zeros(4, dtype=np.float64))  # element types differ
+    with pytest.raises(ValueError):
+        c.Alltoall(a4, a8)                        # send and recv must match
+    with pytest.raises(ValueError):
+        c.Reduce(a4, a8, mpi.SUM, 0)
+    with pytest.raises(TypeError):
+        c.Allreduce([1.0, 2.0], a4)               # not a typed buffer: never silently converted
+    with pytest.raises(TypeError):
+        c.Bcast("immutable", 0)                   # Bcast needs a mutable buffer
+    with pytest.raises(ValueError):
+        mpi.DeviceSlice.__getitem__(mpi.DeviceSlice(8, np.float32, ptr=4096, owner=False), slice(0, 8, 2))  # contiguous slices only
+
+
+def test_data_calls_before_init_report_not_initialised():
+    lib = L.load()
+    assert lib.b200mpi_rank() == -1 and lib.b200mpi_size() == 0       # mpi.go:110-118
+    x = np.zeros(4, dtype=np.float32)
+    for call in (lambda: mpi.Allreduce(x, x), lambda: mpi.Send(x, 0, 1), lambda: mpi.Isend(x, 0, 1), lambda: mpi.Wait(0, 1),
+                 lambda: mpi.Reduce(x, x, mpi.SUM, 0), lambda: mpi.Barrier()):
+        with pytest.raises(mpi.MpiError) as e:
+            call()
+        assert e.value.code == L.ERR_NOT_INIT
