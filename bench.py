@@ -286,8 +286,8 @@ def main():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-nccl", action="store_true")
-    ap.add_argument("--deadline", type=int, default=420, help="seconds after which a partial contract line is printed and the run ends")
-    ap.add_argument("--nccl-deadline", type=int, default=75, help="seconds the NCCL comparison may take before it is abandoned")
+    ap.add_argument("--deadline", type=int, default=300, help="seconds after which a partial contract line is printed and the run ends")
+    ap.add_argument("--nccl-deadline", type=int, default=60, help="seconds the NCCL comparison may take before it is abandoned")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
