@@ -184,7 +184,7 @@ def reference_arm(n, count, dtype, steps, warmup, budget_s=90.0):
 
 
 # ------------------------------------------------------------------------------------------------
-def nccl_comparison(lib, L, mpi, rank, n, local, sizes, send_ptr, recv_ptr):
+def nccl_comparison(lib, L, mpi, rank, n, local, sizes, send_ptr, recv_ptr, cross_check=None):
     """NCCL's own allreduce (float32 sum) on the same device buffers and stream, timed with the same
     event stopwatch.  Comparison line only: loaded with ctypes after every product measurement."""
     out = {}
@@ -264,6 +264,13 @@ def nccl_comparison(lib, L, mpi, rank, n, local, sizes, send_ptr, recv_ptr):
             t = float(o[0]) * 1e-3
             out["sizes"][str(nbytes)] = {"us": t * 1e6, "busbw_gbs": nbytes / t / 1e9 * 2 * (n - 1) / n}
         lib.b200mpi_stream_sync()
+        # an independent implementation of the same semantics: NCCL's result for the last (largest) size,
+        # held to the same tolerance against the CPU oracle as this library's own switch path
+        if cross_check is not None:
+            try:
+                out["result_agrees_with_oracle"] = bool(cross_check())
+            except Exception as e:  # noqa: BLE001
+                out["result_agrees_with_oracle"] = "check failed: %s" % e
         nccl.ncclCommDestroy(comm)
         return out
     except Exception as e:  # noqa: BLE001
@@ -835,7 +842,14 @@ def main():
         guard = threading.Timer(args.nccl_deadline, bail)
         guard.daemon = True
         guard.start()
-        secondary["nccl_allreduce_comparison"] = nccl_comparison(lib, L, mpi, rank, n, local, [1024, 1 << 20, S], send.ptr, recv.ptr)
+        def nccl_cross_check():  # recv now holds NCCL's sum of the same inputs (first and last block)
+            ok = True
+            for lo in sorted({0, max(0, count - BLOCK)}):
+                m = min(BLOCK, count - lo)
+                ins = [O.fill_at(dtype, SEED + r, lo, m) for r in range(n)]
+                ok = ok and close(recv[lo:lo + m].to_host(), O.allreduce(ins, order=O.ORDER_F64), ins)
+            return all_ranks(ok)
+        secondary["nccl_allreduce_comparison"] = nccl_comparison(lib, L, mpi, rank, n, local, [1024, 1 << 20, S], send.ptr, recv.ptr, nccl_cross_check)
         guard.cancel()
 
     deadline.cancel()

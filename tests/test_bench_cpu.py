@@ -93,6 +93,17 @@ def test_bench_world_of_2_switch_branches():
     assert d["config"]["nvls"] is True and d["e2e"] is None
 
 
+def test_bench_world_of_2_nccl_comparison_block():
+    """The NCCL comparison block of bench.py (bound with ctypes on a GPU box) against a stand-in with the
+    same five entry points: init, timing loops, the result cross-check against the oracle, no deadline hit."""
+    res = run_bench(2, "--bytes", str(4 << 20), "--steps", "3", "--warmup", "3", "--no-parity", "--no-e2e", extra_env={"FAKE_NCCL": "1"})
+    assert all(rc == 0 for rc, _, _ in res), "\n".join(e[-2500:] for _, _, e in res)
+    d = contract_line(res[0][1])
+    c = d["secondary"]["nccl_allreduce_comparison"]
+    assert c["version"] == 22703 and set(c["sizes"]) == {"1024", "1048576", str(4 << 20)}, c
+    assert c["result_agrees_with_oracle"] is True, c
+
+
 def test_bench_deadline_prints_a_partial_line():
     """--deadline in the past: the sections after the timed region are cut short, rank 0 still prints
     the contract keys and every rank exits 0."""
