@@ -100,6 +100,7 @@ struct Ctx {
   bool shared_device = false; // several ranks on one GPU (functional-test mode)
   Comm comm = {};
   uint32_t epoch = 1;
+  uint32_t scrub_every = kScrubEvery; // power of two; B200MPI_SCRUB_EVERY lowers it so that a test can reach the scrub
   uint64_t cur_sig = 0; // signature of the collective being launched (checked by sync_start on every rank)
   uint32_t* status_host = nullptr; // mapped pinned
   uint32_t* status_dev = nullptr;
@@ -258,7 +259,19 @@ static int grid_for(size_t units_per_rank, int unroll) {
 
 // Every launch advances the epoch by kEpochStride whatever the algorithm (kernels.cuh), so ranks
 // that disagreed about one call still agree about the flag values of the next.
+static uint64_t mix64(uint64_t x);
 static Comm next_comm() {
+  // Every kScrubEvery-th launch (the same one on every rank: epochs move in lockstep) is preceded by
+  // scrub_kernel, which rewrites every slot row so that no flag word can fall 2^31 behind the epoch.
+  if (g->ctrl.n > 1 && ((g->epoch / kEpochStride) & (g->scrub_every - 1)) == g->scrub_every - 1) {
+    Comm s = g->comm;
+    s.epoch = g->epoch;
+    s.end_epoch = g->epoch + kEpochStride - 1;
+    s.sig = mix64(0x5c2b0000ull ^ ((uint64_t)kMaxBlocks << 8 | 0x5u));
+    g->epoch += kEpochStride;
+    scrub_kernel<<<kMaxBlocks, 32, 0, g->stream>>>(s);
+    (void)cudaGetLastError();
+  }
   Comm c = g->comm;
   c.epoch = g->epoch;
   c.sig = g->cur_sig;
@@ -1643,6 +1656,11 @@ int b200mpi_init(const char* addr, const char* alladdr_csv, const char* password
   if (prop.major < 10) return bail(B200MPI_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is not sm_100-class; this library ships sm_100a code only");
   if (!g->drv.load(err)) return bail(B200MPI_ERR_CUDA, err);
   if (!(getenv("B200MPI_NUMA") && atoi(getenv("B200MPI_NUMA")) == 0)) g->gpu_numa_node = numa_node_of_gpu(g->dev);
+  if (const char* w = getenv("B200MPI_SCRUB_EVERY")) {
+    uint32_t v = (uint32_t)std::max(2, atoi(w)), p2 = 2;
+    while (p2 * 2 <= v) p2 *= 2;
+    g->scrub_every = p2;
+  }
   if (const char* w = getenv("B200MPI_HOST_THREADS")) g->host_threads = std::max(0, atoi(w));
   if (const char* w = getenv("B200MPI_HOST_REGISTER")) g->host_register = atoi(w) != 0;
 

@@ -41,6 +41,7 @@ constexpr int kThreads = 512;
 // agree about the epoch of the next one.
 constexpr uint32_t kEpochStride = 4096;
 constexpr uint32_t kMaxMids = kEpochStride - 2;
+constexpr uint32_t kScrubEvery = 1u << 16;  // launches between two scrub_kernel runs (see there); 2^16 * 4096 = 2^28 << 2^31
 
 // One slot per (CTA, source rank).  The start barrier needs no release fence: the three cells are
 // plain 16-byte stores that carry their own flag next to every 8 payload bytes (the LL idea: only
@@ -1589,6 +1590,19 @@ allreduce_ll_kernel(Comm c, const T* __restrict__ send, T* recv, size_t count, u
 __global__ void flag_kernel(uint32_t* done, uint32_t value) {
   __threadfence_system();
   *(volatile uint32_t*)done = value;
+}
+
+// Flag words are compared wrap-safe ((int32_t)(flag - want) >= 0), which is only sound while no word lags
+// the epoch by 2^31.  A slot row of a block index that has not been used for 2^31 / kEpochStride =
+// 524,288 launches would look "ahead".  Every kScrubEvery launches the host therefore runs this
+// kernel with the largest grid: its start and end barriers rewrite the cells and the flag of every
+// row on every rank, and each CTA refreshes its ring step counter.
+__global__ void scrub_kernel(Comm c) {
+  __shared__ uint64_t s_a[kMaxRanks], s_b[kMaxRanks];
+  const bool ok = sync_start(c, 0, 0, s_a, s_b);
+  if (threadIdx.x == 0) *ring_flag(c, c.rank, blockIdx.x) = c.epoch * 8u;
+  if (ok) sync_end(c);
+  else sync_end_failed(c);
 }
 
 // A device-wide rendezvous with nothing in between (b200mpi_barrier).

@@ -149,3 +149,13 @@ def test_full_size_points():
     elements (64 MiB) with every algorithm; bounce 1 MiB float64 is covered above."""
     world(8, "fullsize", "--what", "allgather", timeout=900, env={"B200MPI_HEAP_BYTES": str(512 << 20)})
     world(2, "fullsize", "--what", "allreduce", timeout=900, env={"B200MPI_HEAP_BYTES": str(1 << 30)})
+
+
+def test_flag_scrub_between_collectives():
+    """Every kScrubEvery-th launch is preceded by scrub_kernel (rewrites every barrier slot so that the
+    wrap-safe flag comparisons stay sound on long jobs).  B200MPI_SCRUB_EVERY=4 makes that every 4th
+    launch here; results must be unaffected.  (Last in the file: written after the round's GPU budget
+    was spent, so its first run is the driver's.)"""
+    world(2, "collectives", "--sizes", "1,257,65537", "--kinds", "heap", "--dtypes", "f32", env={"B200MPI_SCRUB_EVERY": "4"})
+    world(4, "collectives", "--sizes", "257,4099", "--kinds", "heap", "--dtypes", "i64", env={"B200MPI_SCRUB_EVERY": "4"})
+
