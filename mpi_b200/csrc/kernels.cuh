@@ -41,7 +41,8 @@ constexpr int kThreads = 512;
 // agree about the epoch of the next one.
 constexpr uint32_t kEpochStride = 4096;
 constexpr uint32_t kMaxMids = kEpochStride - 2;
-constexpr uint32_t kScrubEvery = 1u << 16;  // launches between two scrub_kernel runs (see there); 2^16 * 4096 = 2^28 << 2^31
+constexpr uint32_t kScrubEvery = 1u << 14;  // launches between two scrub_kernel runs (see there): barrier flags then lag by at most
+                                            // 2^14 * 4096 = 2^26, ring step counters (epoch * 8) by 2^29, both far below 2^31
 
 // One slot per (CTA, source rank).  The start barrier needs no release fence: the three cells are
 // plain 16-byte stores that carry their own flag next to every 8 payload bytes (the LL idea: only
@@ -1594,7 +1595,8 @@ __global__ void flag_kernel(uint32_t* done, uint32_t value) {
 
 // Flag words are compared wrap-safe ((int32_t)(flag - want) >= 0), which is only sound while no word lags
 // the epoch by 2^31.  A slot row of a block index that has not been used for 2^31 / kEpochStride =
-// 524,288 launches would look "ahead".  Every kScrubEvery launches the host therefore runs this
+// 524,288 launches would look "ahead" (65,536 for the ring step counters, which count epoch * 8).
+// Every kScrubEvery launches the host therefore runs this
 // kernel with the largest grid: its start and end barriers rewrite the cells and the flag of every
 // row on every rank, and each CTA refreshes its ring step counter.
 __global__ void scrub_kernel(Comm c) {
