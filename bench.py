@@ -162,25 +162,33 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def reference_arm(n, count, dtype, steps, warmup, budget_s=90.0):
-    """Times oracle/ref_tcp.c (restated reference) with n ranks (2 threads each) on this host: the
-    same S, n, steps and warm-up as the GPU arm unless a one-step probe says that takes longer than
-    budget_s, in which case steps/warm-up are cut (and reported)."""
+def reference_arm(n, count, dtype, steps, warmup, budget_s=90.0, processes=True):
+    """Times oracle/ref_tcp.c (restated reference) on this host with n ranks, one OS process per rank
+    as gompirun starts them (2 threads each: Send runs beside Receive): the same S, n, steps and warm-up
+    as the GPU arm unless a one-step probe says that takes longer than budget_s, in which case
+    steps/warm-up are cut (and reported)."""
     from oracle import oracle as O
     t0 = time.time()
-    probe, _ = O.ref_bench(O.COLL_ALLREDUCE, dtype, n, count, iters=1, warmup=0, seed=SEED)
+    procs = processes
+    if procs:
+        try:
+            probe, _ = O.ref_bench(O.COLL_ALLREDUCE, dtype, n, count, iters=1, warmup=0, seed=SEED, processes=True)
+        except RuntimeError:  # fork not possible here: ranks as threads of one process
+            procs = False
+    if not procs:
+        probe, _ = O.ref_bench(O.COLL_ALLREDUCE, dtype, n, count, iters=1, warmup=0, seed=SEED)
     k, w = steps, warmup
     if probe * (k + w) > budget_s:
         w = 1
         k = int(max(1, min(steps, (budget_s - probe) // max(probe, 1e-9))))
-    secs, out = O.ref_bench(O.COLL_ALLREDUCE, dtype, n, count, iters=k, warmup=w, seed=SEED)
+    secs, out = O.ref_bench(O.COLL_ALLREDUCE, dtype, n, count, iters=k, warmup=w, seed=SEED, processes=procs)
     ok = True
     for lo in range(0, count, BLOCK):  # whole-buffer check, block by block
         m = min(BLOCK, count - lo)
         want = O.allreduce([O.fill_at(dtype, SEED + r, lo, m) for r in range(n)], order=O.ORDER_F64)
         ok = ok and bool(np.allclose(out[lo:lo + m], want, rtol=1e-6, atol=0))
     return {"secs": secs, "ok": ok, "steps": k, "warmup": w, "capped": (k, w) != (steps, warmup), "probe_s": probe, "wall_s": time.time() - t0,
-            "cores": min(2 * n, host_cores())}
+            "cores": min(2 * n, host_cores()), "ranks_as": "processes" if procs else "threads"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -325,7 +333,7 @@ def main():
                        "note": "restated reference path (oracle/ref_tcp.c): gob encode/decode + 2 TCP conns per pair + ack, ring allreduce composed from Send/Receive; same bytes per rank and rank count as the GPU arm"
                                + ("; steps/warm-up cut to keep the run near 90 s (one step takes %.2f s)" % r["probe_s"] if r["capped"] else "")},
             "cpu_baseline": {"value": val, "unit": "GB/s", "cores": r["cores"], "kind": "port",
-                             "sample": "%d MiB per rank, %d timed iterations, %d ranks x 2 threads" % (S >> 20, r["steps"], rn), "parity_ok": r["ok"]},
+                             "sample": "%d MiB per rank, %d timed iterations, %d rank %s x 2 threads" % (S >> 20, r["steps"], rn, r["ranks_as"]), "parity_ok": r["ok"]},
             "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "host_cores": host_cores(), "wall_s": r["wall_s"],
         }
@@ -808,7 +816,7 @@ def main():
     cpu = None
     if rank == 0 and n == 1 and not args.no_cpu_baseline:
         sample = min(args.cpu_sample_bytes, S)
-        r = reference_arm(1, sample // 4, dtype, 3, 1, budget_s=30.0)
+        r = reference_arm(1, sample // 4, dtype, 3, 1, budget_s=30.0, processes=False)  # no fork from a process that holds a CUDA context
         cpu = {"value": sample / r["secs"] / 1e9, "unit": "GB/s", "cores": r["cores"], "kind": "port",
                "sample": "%d MiB, %d iterations, world of 1 = Send/Receive to self (gob encode + decode); the full-size run is `--impl reference`" % (sample >> 20, r["steps"]), "parity_ok": r["ok"]}
 

@@ -61,6 +61,7 @@ def lib():
         L.gob_put_struct_typedef.argtypes = [c.c_void_p, c.c_char_p, c.c_int, c.c_int, c.POINTER(c.c_char_p), c.POINTER(c.c_int)]
         L.gob_put_struct_typedef.restype = c.c_size_t
         L.ref_bench.argtypes = [c.c_int, c.c_int, c.c_int, c.c_size_t, c.c_int, c.c_int, c.c_uint64, c.POINTER(c.c_double), c.c_void_p]
+        L.ref_bench_procs.argtypes = L.ref_bench.argtypes
         _lib = L
     return _lib
 
@@ -228,13 +229,15 @@ def gob_decode(stream, dtype, capacity):
 
 
 # ---- restated reference TCP path ---------------------------------------------------------------
-def ref_bench(coll, dtype, n, count, iters=3, warmup=1, seed=0xB2000000):
-    """Times the restated reference path; returns (seconds_per_iter, rank 0's final buffer)."""
+def ref_bench(coll, dtype, n, count, iters=3, warmup=1, seed=0xB2000000, processes=False):
+    """Times the restated reference path; returns (seconds_per_iter, rank 0's final buffer).
+    processes=True: one OS process per rank (as gompirun starts them) instead of threads."""
     dt = np.dtype(dtype)
     total = count * n if coll == COLL_ALLGATHER else count
     out = np.empty(total, dtype=dt)
     secs = ctypes.c_double(0)
-    rc = lib().ref_bench(coll, NP2DT[dt], n, count, iters, warmup, ctypes.c_uint64(seed), ctypes.byref(secs), out.ctypes.data)
+    fn = lib().ref_bench_procs if processes else lib().ref_bench
+    rc = fn(coll, NP2DT[dt], n, count, iters, warmup, ctypes.c_uint64(seed), ctypes.byref(secs), out.ctypes.data)
     if rc:
         raise RuntimeError("ref_bench failed rc=%d" % rc)
     return secs.value, out

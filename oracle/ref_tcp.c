@@ -16,8 +16,10 @@
  *   ref_recv       read one envelope from the listen socket (network.go:609), Raw.GobDecode copies
  *                  the payload out (mpi.go:83-91), write the ack {Tag} (network.go:617-621),
  *                  gob-decode into the typed destination (network.go:594-601)
- * Ranks are threads of one process (the reference uses one OS process per rank; the bytes still
- * cross the kernel's TCP stack, which is what is being measured); ranks are not pinned.
+ * ref_bench runs the ranks as threads of one process; ref_bench_procs forks one OS process per rank
+ * (what the reference does: gompirun.go:85 starts one process per rank), with the sockets created
+ * before the fork and a process-shared barrier around every step.  Either way the bytes cross the
+ * kernel's TCP stack, which is what is being measured; ranks are not pinned.
  * Collectives do not exist in the reference (mpi.go:130): they are composed from Send/Receive
  * the way a user of the reference would -- ring allreduce / allgather, root-sends-to-all bcast --
  * with Send running concurrently with Receive (the "go mpi.Send(...)" idiom of
@@ -33,7 +35,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
 #include <sys/socket.h>
+#include <sys/wait.h>
 #include <time.h>
 #include <unistd.h>
 
@@ -239,7 +243,14 @@ static int send_wait(rank_ctx* c) {
 /* ---- world --------------------------------------------------------------------------------- */
 static void reader_init(reader* r, int fd) { r->fd = fd; r->cap = 1u << 16; r->buf = (uint8_t*)malloc(r->cap); r->lo = r->hi = 0; }
 
-world* ref_world_create(int n) {
+static void start_helper(rank_ctx* c) {
+  pthread_mutex_init(&c->mu, NULL);
+  pthread_cond_init(&c->cv, NULL);
+  pthread_create(&c->helper, NULL, helper_main, c);
+}
+
+/* sockets only: the per-rank helper threads are started by the caller (threads do not survive fork) */
+static world* world_sockets(int n) {
   if (n < 1 || n > MAXR) return NULL;
   world* w = (world*)calloc(1, sizeof(world));
   w->n = n;
@@ -278,12 +289,13 @@ world* ref_world_create(int n) {
       reader_init(&w->r[j].rd_listen[i], a);
     }
   for (int i = 0; i < n; ++i) close(lst[i]);
-  for (int i = 0; i < n; ++i) {
-    rank_ctx* c = &w->r[i];
-    pthread_mutex_init(&c->mu, NULL);
-    pthread_cond_init(&c->cv, NULL);
-    pthread_create(&c->helper, NULL, helper_main, c);
-  }
+  return w;
+}
+
+world* ref_world_create(int n) {
+  world* w = world_sockets(n);
+  if (!w) return NULL;
+  for (int i = 0; i < n; ++i) start_helper(&w->r[i]);
   return w;
 }
 
@@ -458,3 +470,67 @@ int ref_bench(int coll, int dtype, int n, size_t count, int iters, int warmup, u
   if (seconds_per_iter) *seconds_per_iter = secs;
   return rc;
 }
+
+/* The same harness with one OS process per rank (gompirun.go:85).  The sockets of the whole mesh are
+ * created first, then n children are forked; child r closes the other ranks' ends, starts its helper
+ * thread and runs bench_main for rank r.  The step barrier, the timing word and rank 0's result live in
+ * a shared anonymous mapping.  Returns 0 on success. */
+typedef struct {
+  pthread_barrier_t bar;
+  double secs;
+  int rc[MAXR];
+} shared_hdr;
+
+int ref_bench_procs(int coll, int dtype, int n, size_t count, int iters, int warmup, uint64_t seed, double* seconds_per_iter, void* out_rank0) {
+  if (n < 1 || n > MAXR) return -1;
+  const size_t total = (coll == COLL_ALLGATHER ? count * (size_t)n : count) * esz(dtype);
+  const size_t map_len = sizeof(shared_hdr) + total + 64;
+  shared_hdr* sh = (shared_hdr*)mmap(NULL, map_len, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+  if (sh == MAP_FAILED) return -1;
+  pthread_barrierattr_t ba;
+  pthread_barrierattr_init(&ba);
+  pthread_barrierattr_setpshared(&ba, PTHREAD_PROCESS_SHARED);
+  pthread_barrier_init(&sh->bar, &ba, (unsigned)n);
+  sh->secs = 0;
+  for (int r = 0; r < n; ++r) sh->rc[r] = -99;
+  world* w = world_sockets(n);
+  if (!w) { munmap(sh, map_len); return -1; }
+  pid_t pid[MAXR];
+  for (int r = 0; r < n; ++r) {
+    pid[r] = fork();
+    if (pid[r] == 0) {
+      for (int i = 0; i < n; ++i) { /* keep only this rank's ends of the mesh */
+        if (i == r) continue;
+        for (int j = 0; j < n; ++j) {
+          if (w->r[i].dial[j] >= 0) close(w->r[i].dial[j]);
+          if (w->r[i].listen[j] >= 0) close(w->r[i].listen[j]);
+        }
+      }
+      start_helper(&w->r[r]);
+      job j = {w, r, coll, dtype, count, iters, warmup, seed, &sh->bar, &sh->secs, r == 0 ? (void*)(sh + 1) : NULL, 0};
+      bench_main(&j);
+      sh->rc[r] = j.rc;
+      _exit(0);
+    }
+    if (pid[r] < 0) { sh->rc[r] = -1; }
+  }
+  /* the parent holds no end of the mesh */
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) {
+      if (w->r[i].dial[j] >= 0) close(w->r[i].dial[j]);
+      if (w->r[i].listen[j] >= 0) close(w->r[i].listen[j]);
+    }
+  int rc = 0;
+  for (int r = 0; r < n; ++r) {
+    int st = 0;
+    if (pid[r] > 0) waitpid(pid[r], &st, 0);
+    if (pid[r] <= 0 || !WIFEXITED(st) || WEXITSTATUS(st) != 0 || sh->rc[r] != 0) rc = -2;
+  }
+  if (seconds_per_iter) *seconds_per_iter = sh->secs;
+  if (out_rank0 && rc == 0) memcpy(out_rank0, sh + 1, total);
+  pthread_barrier_destroy(&sh->bar);
+  munmap(sh, map_len);
+  free(w);
+  return rc;
+}
+
